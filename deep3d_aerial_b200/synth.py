@@ -1,0 +1,137 @@
+"""Seeded synthetic scenes for parity tests and the benchmark.
+
+Nothing here is on the hot path: it only manufactures inputs with the tensor
+contract that the reference's dataset hands to the cascade networks
+(reference `mvs/mvs_cas/datasets/cas_normal_eval.py:138-162`): per-view 4x4
+projection matrices ``[[K @ [R|t]], [0,0,0,1]]`` with rows 0-1 divided by
+{4,2,1} for stage {1,2,3}, a ``[dmin, dmax]`` depth range and per-view feature
+maps.  The rig is WHU-OMVS shaped: a nadir reference camera and source cameras
+on a cross (+-x, +-y) converging on the scene centre.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+
+@dataclass
+class Rig:
+    """A reference camera plus V-1 source cameras, full-resolution intrinsics."""
+
+    width: int            # full-resolution image width  (columns)
+    height: int           # full-resolution image height (rows)
+    focal: float
+    z_mean: float
+    dmin: float
+    dmax: float
+    proj_full: np.ndarray  # [V,4,4] float32, K @ [R|t] at full resolution
+
+    def proj(self, scale: int) -> np.ndarray:
+        """Projection matrices for a stage whose features are 1/scale of full res."""
+        p = self.proj_full.copy()
+        p[:, :2, :] = self.proj_full[:, :2, :] / np.float32(scale)
+        return p
+
+    @property
+    def depth_range(self) -> np.ndarray:
+        return np.array([self.dmin, self.dmax], dtype=np.float32)
+
+
+def _rot_y(a):
+    c, s = math.cos(a), math.sin(a)
+    return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], dtype=np.float64)
+
+
+def _rot_x(a):
+    c, s = math.cos(a), math.sin(a)
+    return np.array([[1, 0, 0], [0, c, -s], [0, s, c]], dtype=np.float64)
+
+
+def make_rig(num_views=5, width=1856, height=2752, focal=4000.0, z_mean=500.0,
+             baseline_frac=0.08, range_frac=0.2) -> Rig:
+    """Cross rig: ref at the origin looking down +z, sources at +-baseline on x
+    then y, each rotated about the orthogonal axis so its optical axis passes
+    through (0, 0, z_mean) (convergence atan(baseline/z_mean), 4.6 deg by default)."""
+    K = np.array([[focal, 0, (width - 1) / 2.0],
+                  [0, focal, (height - 1) / 2.0],
+                  [0, 0, 1]], dtype=np.float64)
+    b = baseline_frac * z_mean
+    centres = [np.zeros(3)]
+    rots = [np.eye(3)]
+    offsets = [(+b, 0), (-b, 0), (0, +b), (0, -b), (+b, +b), (-b, -b), (+b, -b), (-b, +b)]
+    for i in range(num_views - 1):
+        ox, oy = offsets[i % len(offsets)]
+        ring = 1 + i // len(offsets)
+        ox, oy = ox * ring, oy * ring
+        c = np.array([ox, oy, 0.0])
+        # world->camera rotation turning the optical axis towards the scene centre
+        R = _rot_y(math.atan2(ox, z_mean)).T @ _rot_x(-math.atan2(oy, z_mean)).T
+        centres.append(c)
+        rots.append(R)
+    projs = []
+    for R, c in zip(rots, centres):
+        E = np.eye(4)
+        E[:3, :3] = R
+        E[:3, 3] = -R @ c
+        P = E.copy()
+        P[:3, :4] = K @ E[:3, :4]
+        projs.append(P.astype(np.float32))
+    return Rig(width=width, height=height, focal=focal, z_mean=z_mean,
+               dmin=(1 - range_frac) * z_mean, dmax=(1 + range_frac) * z_mean,
+               proj_full=np.stack(projs))
+
+
+def tiny_rig(num_views=3, width=160, height=128) -> Rig:
+    """Config 1 of BASELINE.json: f=200, baselines +-0.5, depth 5..15."""
+    return make_rig(num_views=num_views, width=width, height=height, focal=200.0,
+                    z_mean=10.0, baseline_frac=0.05, range_frac=0.5)
+
+
+def make_features(num_views, channels, h, w, seed=0, smooth=False, device="cpu"):
+    """N(0,1) feature maps [V,C,h,w]; `smooth` low-passes them (avg_pool 5x5,
+    re-normalised) so that bilinear errors are not hidden by white noise."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    f = torch.randn(num_views, channels, h, w, generator=g, dtype=torch.float32)
+    if smooth:
+        f = torch.nn.functional.avg_pool2d(f, 5, stride=1, padding=2)
+        f = f / f.std()
+    return f.to(device)
+
+
+def uniform_hypotheses(dmin, dmax, num_depth, device="cpu"):
+    """Stage-1 plane sweep: D fronto-parallel planes, [D]."""
+    return torch.linspace(float(dmin), float(dmax), num_depth, dtype=torch.float32, device=device)
+
+
+def smooth_depth_map(rig: Rig, h, w, seed=0, device="cpu"):
+    """A tilted plane plus a low-frequency sinusoid inside the depth range, [h,w]."""
+    ys = torch.linspace(-1, 1, h).view(h, 1)
+    xs = torch.linspace(-1, 1, w).view(1, w)
+    ph = 0.37 * (seed + 1)
+    mid = 0.5 * (rig.dmin + rig.dmax)
+    amp = 0.25 * (rig.dmax - rig.dmin)
+    d = mid + amp * (0.5 * xs - 0.3 * ys + 0.4 * torch.sin(3.1 * xs + ph) * torch.cos(2.3 * ys - ph))
+    return d.to(torch.float32).to(device)
+
+
+def per_pixel_hypotheses(cur_depth, num_depth, interval):
+    """Stage>=2 hypotheses around `cur_depth` [h,w] -> [D,h,w]
+    (same arithmetic as reference module.py:616-630, stated independently here
+    only to make inputs; parity of the real resampler is tested separately)."""
+    lo = cur_depth - num_depth / 2 * interval
+    hi = cur_depth + num_depth / 2 * interval
+    step = (hi - lo) / (num_depth - 1)
+    k = torch.arange(num_depth, dtype=cur_depth.dtype, device=cur_depth.device).view(-1, 1, 1)
+    return lo.unsqueeze(0) + k * step.unsqueeze(0)
+
+
+def planted_logits(num_depth, h, w, seed=0, device="cpu"):
+    """Kernel-2 input: 4*N(0,1) with a +8 peak planted at a random plane per pixel."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = 4.0 * torch.randn(num_depth, h, w, generator=g, dtype=torch.float32)
+    peak = torch.randint(0, num_depth, (1, h, w), generator=g)
+    x.scatter_add_(0, peak, torch.full((1, h, w), 8.0))
+    return x.to(device)
