@@ -1,0 +1,37 @@
+// Shared helpers for libd3dsweep (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "d3d_sweep.h"
+
+namespace d3d {
+
+// error plumbing (abi.cu)
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);
+void count_launch(int n = 1);
+
+constexpr int kMaxSrc = 8;  // V-1
+
+// Kernel parameters of the fused sweep (by value: lands in the constant bank).
+struct SweepParams {
+    const float* __restrict__ feats;    // [V,H,W,C]
+    const float* __restrict__ pose;     // [V-1,4,4]
+    const float* __restrict__ hyps;     // [D] or [D,H,W]
+    const float* __restrict__ weights;  // [V-1,H,W] or null
+    float* __restrict__ out;
+    long long out_sc, out_sd;
+    int C, H, W, HW;
+    int d_begin, d_end;   // planes computed by this launch
+    int d_chunk;          // planes per blockIdx.y
+    int lpp_log2;         // log2(lanes per pixel) = log2(C / CPT)
+    int perpix;           // hyps layout
+    int groups, eps_num;
+    float inv_half_w, inv_half_h;  // 1/((W-1)/2), 1/((H-1)/2)   (module.py:543-544)
+    float wm1, hm1;                // W-1, H-1                   (GridSampler.h:27-32)
+};
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+}  // namespace d3d

@@ -1,0 +1,282 @@
+// Fused depth regression: softmax over the D planes of a logit volume, expected depth, photometric
+// confidence, arg-max plane, optional UCS-Net spread and optional next-stage hypotheses, in ONE
+// pass over the logits (4 B/voxel of HBM traffic; the reference makes 4-8 passes).
+//
+//   one thread = one pixel; consecutive lanes = consecutive x, so every plane access of a warp is a
+//   single 128-byte line; planes are consumed 8 at a time (8 independent loads in flight per
+//   thread) with one online-softmax rescale per group.
+//
+// Reference lines: cas_mvsnet.py:69-76 (softmax, regression, 4-plane window confidence),
+// msrednet.py:234-238 / adamvs.py:306-310,478-483 (max-prob confidence), adamvs.py:514-529 /
+// msrednet.py:418-437 (streaming un-normalised exp), module.py:605-613 (depth_regression incl. the
+// bilinear resize of 4-D hypotheses), ucsnet.py:148-149 (exp_variance), module.py:616-630
+// (next-stage samples).
+#include "common.cuh"
+
+namespace d3d {
+
+struct RegressParams {
+    const float* __restrict__ logits;
+    const float* __restrict__ hyps;
+    float* __restrict__ depth;
+    float* __restrict__ conf;
+    int* __restrict__ index;
+    float* __restrict__ state;
+    float* __restrict__ expvar;
+    float* __restrict__ next_hyps;
+    long long stride_d;
+    int D, H, W, HW;
+    int d_begin, d_count;
+    int conf_mode, hyps_mode, hh, hw, finalize;
+    int identity;           // D3D_SOFTMAX_NONE: the input is a probability volume
+    int next_nd;
+    float next_half_span;   // (float)(next_nd/2 * interval), module.py:619-620
+    float lamb;
+    float scale_h, scale_w; // hh/H, hw/W for the align_corners=False resize
+};
+
+constexpr int kGroup = 8;
+
+// Bilinear tap of ATen's upsample_bilinear2d (align_corners=False):
+//   src = scale*(dst+0.5)-0.5 clamped at 0;  i1 = (int)src;  lambda1 = src-i1;  lambda0 = 1-lambda1
+struct ResizeTap {
+    int o00, o01, o10, o11;
+    float h0, h1, w0, w1;
+};
+
+__device__ __forceinline__ ResizeTap make_tap(int y, int x, const RegressParams& p) {
+    float sy = fmaxf(p.scale_h * ((float)y + 0.5f) - 0.5f, 0.f);
+    float sx = fmaxf(p.scale_w * ((float)x + 0.5f) - 0.5f, 0.f);
+    int y1 = (int)sy, x1 = (int)sx;
+    int yp = (y1 < p.hh - 1) ? 1 : 0, xp = (x1 < p.hw - 1) ? 1 : 0;
+    ResizeTap t;
+    t.h1 = sy - (float)y1; t.h0 = 1.f - t.h1;
+    t.w1 = sx - (float)x1; t.w0 = 1.f - t.w1;
+    t.o00 = y1 * p.hw + x1;
+    t.o01 = t.o00 + xp;
+    t.o10 = t.o00 + yp * p.hw;
+    t.o11 = t.o10 + xp;
+    return t;
+}
+
+template <int HYPS>
+__device__ __forceinline__ float hyp_at(const RegressParams& p, int k, int pix, const ResizeTap& t) {
+    if (HYPS == D3D_HYPS_UNIFORM) return __ldg(p.hyps + k);
+    if (HYPS == D3D_HYPS_PER_PIXEL) return __ldg(p.hyps + (size_t)k * p.HW + pix);
+    const float* q = p.hyps + (size_t)k * p.hh * p.hw;
+    return t.h0 * (t.w0 * __ldg(q + t.o00) + t.w1 * __ldg(q + t.o01)) +
+           t.h1 * (t.w0 * __ldg(q + t.o10) + t.w1 * __ldg(q + t.o11));
+}
+
+__device__ __forceinline__ void emit_next(const RegressParams& p, int pix, float depth) {
+    if (p.next_nd <= 0) return;
+    // module.py:619-627: lo = cur - nd/2*itv; hi = cur + nd/2*itv; step = (hi-lo)/(nd-1); lo + k*step
+    float lo = __fsub_rn(depth, p.next_half_span);
+    float hi = __fadd_rn(depth, p.next_half_span);
+    float step = __fdiv_rn(__fsub_rn(hi, lo), (float)(p.next_nd - 1));
+    for (int k = 0; k < p.next_nd; ++k)
+        p.next_hyps[(size_t)k * p.HW + pix] = __fadd_rn(lo, __fmul_rn((float)k, step));
+}
+
+// ---- F.softmax flavour -------------------------------------------------------------------------
+template <int HYPS>
+__global__ void __launch_bounds__(256) regress_softmax_kernel(const RegressParams p) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= p.HW) return;
+    ResizeTap tap = {};
+    if (HYPS == D3D_HYPS_RESIZED) tap = make_tap(pix / p.W, pix % p.W, p);
+    const float* lg = p.logits + pix;
+
+    float m = -INFINITY;       // running max
+    float s = 0.f;             // sum exp(x-m)
+    float sd = 0.f;            // sum exp(x-m) * (d - dref)
+    float sk = 0.f;            // sum exp(x-m) * k
+    float sdd = 0.f;           // sum exp(x-m) * (d - dref)^2
+    int arg = 0;
+    const float dref = hyp_at<HYPS>(p, 0, pix, tap);   // shift keeps the sums well conditioned
+    const bool want_var = p.expvar != nullptr;
+
+    for (int k0 = 0; k0 < p.D; k0 += kGroup) {
+        float x[kGroup], d[kGroup];
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+            int k = k0 + j;
+            bool ok = k < p.D;
+            x[j] = ok ? __ldg(lg + (size_t)k * p.stride_d) : -INFINITY;
+            d[j] = ok ? hyp_at<HYPS>(p, k, pix, tap) : dref;
+        }
+        float gm = x[0];
+#pragma unroll
+        for (int j = 1; j < kGroup; ++j) gm = fmaxf(gm, x[j]);
+        if (gm > m) {
+            float r = expf(m - gm);   // 0 on the first group (m = -inf)
+            s *= r; sd *= r; sk *= r; sdd *= r;
+#pragma unroll
+            for (int j = kGroup - 1; j >= 0; --j)
+                if (x[j] == gm) arg = k0 + j;          // first plane reaching the new maximum
+            m = gm;
+        }
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+            float e = expf(x[j] - m);
+            float dc = d[j] - dref;
+            s += e;
+            sd = fmaf(e, dc, sd);
+            sk = fmaf(e, (float)(k0 + j), sk);
+            if (want_var) sdd = fmaf(e * dc, dc, sdd);
+        }
+    }
+    const float inv = 1.f / s;
+    const float mean_c = sd * inv;
+    const float depth = dref + mean_c;
+    p.depth[pix] = depth;
+    float conf;
+    int idx;
+    if (p.conf_mode == D3D_CONF_MAX_PROB) {
+        conf = inv;          // exp(max-max)/sum
+        idx = arg;
+    } else {
+        // cas_mvsnet.py:72-76: i = clamp(long(sum p*k)); conf = p[i-1]+p[i]+p[i+1]+p[i+2]
+        idx = (int)(sk * inv);
+        idx = max(0, min(idx, p.D - 1));
+        float w = 0.f;
+#pragma unroll
+        for (int j = -1; j <= 2; ++j) {
+            int k = idx + j;
+            if (k >= 0 && k < p.D) w += expf(__ldg(lg + (size_t)k * p.stride_d) - m);
+        }
+        conf = w * inv;
+    }
+    p.conf[pix] = conf;
+    if (p.index) p.index[pix] = idx;
+    if (want_var) {
+        float var = fmaxf(sdd * inv - mean_c * mean_c, 0.f);
+        p.expvar[pix] = p.lamb * sqrtf(var);
+    }
+    emit_next(p, pix, depth);
+}
+
+// ---- streaming un-normalised exp flavour ---------------------------------------------------------
+template <int HYPS>
+__global__ void __launch_bounds__(256) regress_rawexp_kernel(const RegressParams p) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= p.HW) return;
+    ResizeTap tap = {};
+    if (HYPS == D3D_HYPS_RESIZED) tap = make_tap(pix / p.W, pix % p.W, p);
+    const float* lg = p.logits + pix;
+    float s = 0.f, acc = 0.f, mx = 0.f;      // adamvs.py:456-462: zero-initialised accumulators
+    if (p.d_begin > 0) {
+        s = p.state[pix];
+        acc = p.state[(size_t)p.HW + pix];
+        mx = p.state[2 * (size_t)p.HW + pix];
+    }
+    for (int k0 = 0; k0 < p.d_count; k0 += kGroup) {
+        float x[kGroup], d[kGroup];
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+            int k = k0 + j;
+            bool ok = k < p.d_count;
+            x[j] = ok ? __ldg(lg + (size_t)k * p.stride_d) : -INFINITY;
+            d[j] = ok ? hyp_at<HYPS>(p, p.d_begin + k, pix, tap) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+            if (k0 + j < p.d_count) {
+                float e = p.identity ? x[j] : expf(x[j]);   // adamvs.py:514, no max subtraction
+                mx = (mx < e) ? e : mx;            // :516-517
+                acc = __fadd_rn(__fmul_rn(d[j], e), acc);   // :522
+                s = s + e;                         // :525
+            }
+        }
+    }
+    if (p.state) {
+        p.state[pix] = s;
+        p.state[(size_t)p.HW + pix] = acc;
+        p.state[2 * (size_t)p.HW + pix] = mx;
+    }
+    if (p.finalize) {
+        float tot = s + 1e-10f;                    // :527-529
+        float depth = p.identity ? acc : acc / tot;
+        p.depth[pix] = depth;
+        p.conf[pix] = p.identity ? mx : mx / tot;
+        emit_next(p, pix, depth);
+    }
+}
+
+template <int HYPS>
+static int launch_regress(const RegressParams& p, int softmax_mode, cudaStream_t stream) {
+    dim3 grid((p.HW + 255) / 256);
+    if (softmax_mode == D3D_SOFTMAX_STABLE)
+        regress_softmax_kernel<HYPS><<<grid, 256, 0, stream>>>(p);
+    else
+        regress_rawexp_kernel<HYPS><<<grid, 256, 0, stream>>>(p);
+    count_launch();
+    return check_launch("regress_kernel");
+}
+
+}  // namespace d3d
+
+using namespace d3d;
+
+extern "C" int d3d_depth_regress(const D3dRegressArgs* a, void* cuda_stream) {
+    if (!a) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: args is NULL");
+    if (a->struct_size != sizeof(D3dRegressArgs))
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: struct_size %u != %zu", a->struct_size,
+                    sizeof(D3dRegressArgs));
+    if (a->num_depth <= 0 || a->height <= 0 || a->width <= 0)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: non-positive extent D=%d H=%d W=%d", a->num_depth,
+                    a->height, a->width);
+    if ((long long)a->height * a->width > INT32_MAX)
+        return fail(D3D_ERR_UNSUPPORTED, "d3d_depth_regress: H*W exceeds 2^31-1");
+    if (!a->logits || !a->hyps) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: logits/hyps is NULL");
+    if (a->softmax_mode < D3D_SOFTMAX_STABLE || a->softmax_mode > D3D_SOFTMAX_NONE)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: unknown softmax_mode %d", a->softmax_mode);
+    if (a->conf_mode != D3D_CONF_MAX_PROB && a->conf_mode != D3D_CONF_WINDOW4)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: unknown conf_mode %d", a->conf_mode);
+    if (a->hyps_mode < D3D_HYPS_UNIFORM || a->hyps_mode > D3D_HYPS_RESIZED)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: unknown hyps_mode %d", a->hyps_mode);
+    if (a->hyps_mode == D3D_HYPS_RESIZED && (a->hyps_height <= 0 || a->hyps_width <= 0))
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: resized hypotheses need hyps_height/width");
+    int d_begin = a->d_begin, d_count = a->d_count <= 0 ? a->num_depth - a->d_begin : a->d_count;
+    if (d_begin < 0 || d_count <= 0 || d_begin + d_count > a->num_depth)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: plane slice [%d,+%d) outside 0..%d", d_begin, d_count,
+                    a->num_depth);
+    const bool raw = a->softmax_mode != D3D_SOFTMAX_STABLE;
+    const bool whole = d_begin == 0 && d_count == a->num_depth;
+    if (!raw && !whole)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: plane slices need D3D_SOFTMAX_RAW_EXP");
+    if (raw && a->conf_mode != D3D_CONF_MAX_PROB)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: RAW_EXP only defines the max-prob confidence");
+    if (raw && !whole && !a->state)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: a plane slice needs the state buffer");
+    if (raw && a->exp_variance)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: exp_variance needs D3D_SOFTMAX_STABLE");
+    const int finalize = raw ? (a->finalize != 0) : 1;
+    if (finalize && (!a->depth || !a->conf))
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: depth/conf output is NULL");
+    if (a->next_num_depth > 0 && !a->next_hyps)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: next_hyps is NULL");
+    if (a->next_num_depth == 1)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: next_num_depth must be >= 2");
+
+    RegressParams p;
+    p.logits = a->logits; p.hyps = a->hyps; p.depth = a->depth; p.conf = a->conf; p.index = a->index;
+    p.state = a->state; p.expvar = a->exp_variance; p.next_hyps = a->next_hyps;
+    p.D = a->num_depth; p.H = a->height; p.W = a->width; p.HW = a->height * a->width;
+    p.stride_d = a->logits_stride_d > 0 ? a->logits_stride_d : p.HW;
+    p.d_begin = d_begin; p.d_count = d_count;
+    p.conf_mode = a->conf_mode; p.hyps_mode = a->hyps_mode;
+    p.hh = a->hyps_height; p.hw = a->hyps_width; p.finalize = finalize;
+    p.identity = a->softmax_mode == D3D_SOFTMAX_NONE;
+    p.next_nd = a->next_num_depth > 0 ? a->next_num_depth : 0;
+    p.next_half_span = (float)((double)p.next_nd / 2.0 * a->next_interval);
+    p.lamb = a->lamb;
+    p.scale_h = p.hh > 0 ? (float)p.hh / (float)p.H : 1.f;
+    p.scale_w = p.hw > 0 ? (float)p.hw / (float)p.W : 1.f;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    switch (a->hyps_mode) {
+        case D3D_HYPS_UNIFORM: return launch_regress<D3D_HYPS_UNIFORM>(p, a->softmax_mode, stream);
+        case D3D_HYPS_PER_PIXEL: return launch_regress<D3D_HYPS_PER_PIXEL>(p, a->softmax_mode, stream);
+        default: return launch_regress<D3D_HYPS_RESIZED>(p, a->softmax_mode, stream);
+    }
+}

@@ -1,0 +1,157 @@
+// Per-stage depth-hypothesis resampling and the feature relayout.
+//
+//   d3d_depth_samples  get_depth_range_samples / get_cur_depth_range_samples (module.py:616-650) and the
+//                      Cas-MVSNet / RED-Net stage glue around it (cas_mvsnet.py:206-226,
+//                      msrednet.py:495-515): bilinear up-sampling of the previous depth to full
+//                      resolution, sampling there, tri-linear down-sampling to the stage -- fused so
+//                      the full-resolution [D,H,W] tensor is never written.
+//   d3d_nchw_to_nhwc   [C,H,W] -> [H,W,C] so that one texel (all channels of one pixel) is contiguous.
+#include "common.cuh"
+
+namespace d3d {
+
+struct SamplesParams {
+    const float* __restrict__ cur;
+    float* __restrict__ out;
+    int mode, D, H, W, HW;
+    int sh, sw, fh, fw;
+    float half_span;        // (float)(D/2 * interval)
+    float dmin, dmax;
+    float up_h, up_w;       // sh/fh, sw/fw : bilinear up-sampling scales (align_corners=False)
+    float dn_h, dn_w;       // fh/H,  fw/W  : tri-linear down-sampling scales
+};
+
+// ATen area_pixel_compute_source_index (align_corners=False): src = scale*(dst+0.5)-0.5, clamped at 0.
+__device__ __forceinline__ void tap1d(float scale, int dst, int in_size, int& i0, int& i1, float& l0, float& l1) {
+    float s = fmaxf(scale * ((float)dst + 0.5f) - 0.5f, 0.f);
+    i0 = min((int)s, in_size - 1);
+    i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+    l1 = s - (float)i0;
+    l0 = 1.f - l1;
+}
+
+__device__ __forceinline__ float upsampled_depth(const SamplesParams& p, int fy, int fx) {
+    int y0, y1, x0, x1;
+    float h0, h1, w0, w1;
+    tap1d(p.up_h, fy, p.sh, y0, y1, h0, h1);
+    tap1d(p.up_w, fx, p.sw, x0, x1, w0, w1);
+    const float* c = p.cur;
+    return h0 * (w0 * __ldg(c + y0 * p.sw + x0) + w1 * __ldg(c + y0 * p.sw + x1)) +
+           h1 * (w0 * __ldg(c + y1 * p.sw + x0) + w1 * __ldg(c + y1 * p.sw + x1));
+}
+
+__global__ void __launch_bounds__(256) depth_samples_kernel(const SamplesParams p) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= p.HW) return;
+    const float dm1 = (float)(p.D - 1);
+    if (p.mode == D3D_SAMPLES_RANGE || (p.mode == D3D_SAMPLES_CASCADE && p.cur == nullptr)) {
+        // module.py:637-645; the trilinear resize of a per-plane constant is that constant
+        float step = __fdiv_rn(__fsub_rn(p.dmax, p.dmin), dm1);
+        for (int k = 0; k < p.D; ++k)
+            p.out[(size_t)k * p.HW + pix] = __fadd_rn(p.dmin, __fmul_rn((float)k, step));
+        return;
+    }
+    if (p.mode == D3D_SAMPLES_AROUND) {
+        float c = __ldg(p.cur + pix);
+        float lo = __fsub_rn(c, p.half_span), hi = __fadd_rn(c, p.half_span);
+        float step = __fdiv_rn(__fsub_rn(hi, lo), dm1);
+        for (int k = 0; k < p.D; ++k)
+            p.out[(size_t)k * p.HW + pix] = __fadd_rn(lo, __fmul_rn((float)k, step));
+        return;
+    }
+    // CASCADE: four full-resolution taps of the tri-linear down-sampling (the depth axis keeps its
+    // size, so its lambda is exactly 0/1), each an up-sampled previous depth
+    const int y = pix / p.W, x = pix - y * p.W;
+    int y0, y1, x0, x1;
+    float h0, h1, w0, w1;
+    tap1d(p.dn_h, y, p.fh, y0, y1, h0, h1);
+    tap1d(p.dn_w, x, p.fw, x0, x1, w0, w1);
+    float lo[4], st[4];
+    const int ys[4] = {y0, y0, y1, y1}, xs[4] = {x0, x1, x0, x1};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float c = upsampled_depth(p, ys[j], xs[j]);
+        lo[j] = __fsub_rn(c, p.half_span);
+        float hi = __fadd_rn(c, p.half_span);
+        st[j] = __fdiv_rn(__fsub_rn(hi, lo[j]), dm1);
+    }
+    for (int k = 0; k < p.D; ++k) {
+        float s[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] = __fadd_rn(lo[j], __fmul_rn((float)k, st[j]));
+        p.out[(size_t)k * p.HW + pix] = h0 * (w0 * s[0] + w1 * s[1]) + h1 * (w0 * s[2] + w1 * s[3]);
+    }
+}
+
+constexpr int kTilePix = 64;
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                          int C, int HW) {
+    extern __shared__ float tile[];   // [C][kTilePix+1]
+    const long long p0 = (long long)blockIdx.x * kTilePix;
+    const int n = C * kTilePix;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int c = i / kTilePix, px = i - c * kTilePix;
+        long long p = p0 + px;
+        tile[c * (kTilePix + 1) + px] = (p < HW) ? __ldg(in + (size_t)c * HW + p) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int px = i / C, c = i - px * C;
+        long long p = p0 + px;
+        if (p < HW) out[(size_t)p * C + c] = tile[c * (kTilePix + 1) + px];
+    }
+}
+
+}  // namespace d3d
+
+using namespace d3d;
+
+extern "C" int d3d_depth_samples(const D3dSamplesArgs* a, void* cuda_stream) {
+    if (!a) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_samples: args is NULL");
+    if (a->struct_size != sizeof(D3dSamplesArgs))
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_samples: struct_size %u != %zu", a->struct_size,
+                    sizeof(D3dSamplesArgs));
+    if (a->mode < D3D_SAMPLES_RANGE || a->mode > D3D_SAMPLES_CASCADE)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_samples: unknown mode %d", a->mode);
+    if (a->num_depth < 2 || a->height <= 0 || a->width <= 0)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_samples: need D >= 2 and positive extent (D=%d H=%d W=%d)",
+                    a->num_depth, a->height, a->width);
+    if ((long long)a->height * a->width > INT32_MAX)
+        return fail(D3D_ERR_UNSUPPORTED, "d3d_depth_samples: H*W exceeds 2^31-1");
+    if (!a->out) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_samples: out is NULL");
+    if (a->mode == D3D_SAMPLES_AROUND && !a->cur)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_samples: AROUND needs cur");
+    if (a->mode == D3D_SAMPLES_CASCADE && a->cur &&
+        (a->src_height <= 0 || a->src_width <= 0 || a->full_height <= 0 || a->full_width <= 0))
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_samples: CASCADE needs src and full extents");
+    SamplesParams p;
+    p.cur = a->cur; p.out = a->out; p.mode = a->mode; p.D = a->num_depth;
+    p.H = a->height; p.W = a->width; p.HW = a->height * a->width;
+    p.sh = a->src_height; p.sw = a->src_width; p.fh = a->full_height; p.fw = a->full_width;
+    p.half_span = (float)((double)a->num_depth / 2.0 * a->interval);
+    p.dmin = a->dmin; p.dmax = a->dmax;
+    p.up_h = p.fh > 0 ? (float)p.sh / (float)p.fh : 1.f;
+    p.up_w = p.fw > 0 ? (float)p.sw / (float)p.fw : 1.f;
+    p.dn_h = (float)p.fh / (float)p.H;
+    p.dn_w = (float)p.fw / (float)p.W;
+    depth_samples_kernel<<<(p.HW + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(p);
+    count_launch();
+    return check_launch("depth_samples_kernel");
+}
+
+extern "C" int d3d_nchw_to_nhwc(const float* in, float* out, int32_t channels, int32_t height, int32_t width,
+                                void* cuda_stream) {
+    if (!in || !out) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_nchw_to_nhwc: NULL pointer");
+    if (channels <= 0 || height <= 0 || width <= 0)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_nchw_to_nhwc: non-positive extent C=%d H=%d W=%d", channels, height,
+                    width);
+    long long hw = (long long)height * width;
+    if (hw > INT32_MAX) return fail(D3D_ERR_UNSUPPORTED, "d3d_nchw_to_nhwc: H*W exceeds 2^31-1");
+    size_t smem = (size_t)channels * (kTilePix + 1) * sizeof(float);
+    if (smem > 48 * 1024) return fail(D3D_ERR_UNSUPPORTED, "d3d_nchw_to_nhwc: C=%d too large", channels);
+    unsigned blocks = (unsigned)((hw + kTilePix - 1) / kTilePix);
+    nchw_to_nhwc_kernel<<<blocks, 256, smem, (cudaStream_t)cuda_stream>>>(in, out, channels, (int)hw);
+    count_launch();
+    return check_launch("nchw_to_nhwc_kernel");
+}

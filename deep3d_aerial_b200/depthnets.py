@@ -1,0 +1,243 @@
+"""Drop-in replacements for the `DepthNet` / `InferDepthNet` forward passes of the reference's cascade
+networks (SURVEY.md §8b level b3) -- same signatures, asserts, return-dict keys and list quirks -- with
+the warp + aggregation and the softmax + regression done by libd3dsweep.  The CNN regularisers are
+NOT here: they are passed in (Cas-MVSNet, RED-Net, UCS-Net) or looked up on `self` (`self.reg`,
+`self.reg_fuse` of the reference's AdaMVS InferDepthNet) and run in PyTorch, unchanged.
+
+    cas_depthnet_forward      cas_mvsnet.py:35-78      DepthNet.forward
+    red_depthnet_forward      msrednet.py:206-241      DepthNet.forward (whole-volume form)
+    red_infer_forward         msrednet.py:377-438      InferDepthNet.forward (plane-at-a-time GRU)
+    ada_infer_forward         adamvs.py:436-531        InferDepthNet.forward
+    ada_depthnet_forward      adamvs.py:247-312        DepthNet.forward (whole-volume form)
+    ucs_compute_depth         ucsnet.py:99-151         compute_depth
+    ucs_uncertainty_samples   ucsnet.py:30-53          uncertainty_aware_samples
+
+`deep3d_aerial_b200.install()` binds these onto the reference's classes; the thin
+`nn.Module` wrappers at the bottom serve callers that build the networks themselves.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import sweep
+
+
+def _check(features, proj_matrices, depth_values, num_depth):
+    assert len(features) == len(proj_matrices), "Different number of images and projection matrices"
+    assert depth_values.shape[1] == num_depth, "depth_values.shape[1]:{}  num_depth:{}".format(
+        depth_values.shape[1], num_depth)
+
+
+def _scene(features, proj_matrices, b):
+    """Channels-last texels [V,H,W,C] and relative poses [V-1,4,4] of batch item b."""
+    texels = sweep.to_texels([f[b] for f in features])
+    pose = sweep.relative_poses(torch.stack([p[b] for p in proj_matrices], 0))
+    return texels, pose
+
+
+def _volume(features, proj_matrices, depth_values, mode, plane_major=False, **kw):
+    """Cost volume for every batch item: [B,Cout,D,H,W] (or [B,D,Cout,H,W] plane-major)."""
+    with torch.no_grad():
+        vols = []
+        for b in range(features[0].shape[0]):
+            texels, pose = _scene(features, proj_matrices, b)
+            w = kw.get("weights")
+            vols.append(sweep.cost_volume(texels, pose, depth_values[b].contiguous(), mode, plane_major=plane_major,
+                                          **{**kw, "weights": None if w is None else w[b]}))
+        return torch.stack(vols, 0) if len(vols) > 1 else vols[0].unsqueeze(0)
+
+
+def _regress(logits, depth_values, **kw):
+    """depth_regress per batch item; logits [B,D,H,W]; returns dict of stacked [B,...] tensors."""
+    outs = [sweep.depth_regress(logits[b], depth_values[b].contiguous(), **kw) for b in range(logits.shape[0])]
+    return {k: torch.stack([o[k] for o in outs], 0) for k in outs[0]}
+
+
+# ------------------------------------------------------------------------------------- Cas-MVSNet
+def cas_depthnet_forward(self, features, proj_matrices, depth_values, num_depth, cost_regularization,
+                         prob_volume_init=None):
+    proj_matrices = torch.unbind(proj_matrices, 1)
+    _check(features, proj_matrices, depth_values, num_depth)
+    volume_variance = _volume(features, proj_matrices, depth_values, sweep.AGG_VARIANCE)     # :46-60
+    cost_reg = cost_regularization(volume_variance)                                             # :63
+    prob_volume_pre = cost_reg.squeeze(1)
+    if prob_volume_init is not None:
+        prob_volume_pre += prob_volume_init
+    with torch.no_grad():
+        r = _regress(prob_volume_pre, depth_values, conf_mode=sweep.CONF_WINDOW4)              # :69-76
+    return {"depth": r["depth"], "photometric_confidence": r["conf"]}
+
+
+# ---------------------------------------------------------------------------------------- RED-Net
+def red_depthnet_forward(self, features, proj_matrices, depth_values, num_depth, cost_regularization,
+                         prob_volume_init=None):
+    proj_matrices = torch.unbind(proj_matrices, 1)
+    _check(features, proj_matrices, depth_values, num_depth)
+    volume_variance = _volume(features, proj_matrices, depth_values, sweep.AGG_VARIANCE)     # :217-230
+    prob_volume_pre = cost_regularization(volume_variance).squeeze(1)
+    if prob_volume_init is not None:
+        prob_volume_pre += prob_volume_init
+    with torch.no_grad():
+        r = _regress(prob_volume_pre, depth_values, conf_mode=sweep.CONF_MAX_PROB)             # :234-238
+    return {"depth": r["depth"], "photometric_confidence": r["conf"]}
+
+
+class _Stream:
+    """Streaming soft-argmax accumulators of the plane-at-a-time models (adamvs.py:456-462, 514-529)."""
+
+    def __init__(self, batch, h, w, device):
+        self.state = [torch.zeros((3, h, w), device=device, dtype=torch.float32) for _ in range(batch)]
+        self.out = None
+
+    def update(self, d, num_depth, reg_cost, depth_values):
+        """reg_cost [B,1,H,W] = the regulariser's output for plane d."""
+        last = d == num_depth - 1
+        outs = []
+        for b in range(reg_cost.shape[0]):
+            outs.append(sweep.depth_regress(reg_cost[b], depth_values[b].contiguous(), softmax_mode=sweep.SOFTMAX_RAW_EXP,
+                                            d_begin=d, state=self.state[b], finalize=last))
+        if last:
+            self.out = {k: torch.stack([o[k] for o in outs], 0) for k in ("depth", "conf")}
+
+
+def red_infer_forward(self, features, proj_matrices, depth_values, num_depth, cost_regularization):
+    proj_matrices = torch.unbind(proj_matrices, 1)
+    _check(features, proj_matrices, depth_values, num_depth)
+    ref = features[0]
+    b_num, _, img_h, img_w = ref.shape
+    dev = ref.device
+    state1 = torch.zeros((b_num, 8, img_h, img_w), device=dev)                                  # :391-394
+    state2 = torch.zeros((b_num, 16, int(img_h / 2), int(img_w / 2)), device=dev)
+    state3 = torch.zeros((b_num, 32, int(img_h / 4), int(img_w / 4)), device=dev)
+    state4 = torch.zeros((b_num, 64, int(img_h / 8), int(img_w / 8)), device=dev)
+    # all D variance planes in one launch, plane-major so each plane is a contiguous [C,H,W] slice
+    volume = _volume(features, proj_matrices, depth_values, sweep.AGG_VARIANCE, plane_major=True)
+    acc = _Stream(b_num, img_h, img_w, dev)
+    for d in range(num_depth):
+        reg_cost, state1, state2, state3, state4 = cost_regularization(volume[:, d], state1, state2, state3, state4)
+        acc.update(d, num_depth, reg_cost, depth_values)                                         # :418-437
+    return {"depth": acc.out["depth"], "photometric_confidence": acc.out["conf"]}
+
+
+# ----------------------------------------------------------------------------------------- AdaMVS
+def ada_infer_forward(self, features, proj_matrices, depth_values, num_depth, confidence_map=None):
+    proj_matrices = torch.unbind(proj_matrices, 1)
+    _check(features, proj_matrices, depth_values, num_depth)
+    ref = features[0]
+    b_num, _, img_h, img_w = ref.shape
+    dev = ref.device
+    n_src = len(features) - 1
+    pair_confidence = []
+    pair_results = []
+    state1 = torch.zeros((b_num, 8, img_h, img_w), device=dev)                                  # :451-452
+    state2 = torch.zeros((b_num, 16, int(img_h / 2), int(img_w / 2)), device=dev)
+    up = 2 if self.in_up else 1
+    acc = _Stream(b_num, img_h * up, img_w * up, dev)
+
+    if confidence_map is None:                                                                  # :465-489
+        pairs = _volume(features, proj_matrices, depth_values, sweep.AGG_PAIR_MEAN)              # [B,V-1,D,h,w]
+        for i in range(n_src):
+            score_volume = self.reg(pairs[:, i])
+            with torch.no_grad():
+                r = _regress(score_volume, depth_values, conf_mode=sweep.CONF_MAX_PROB, want_index=False)
+            pair_results.append(r["depth"])
+            pair_confidence.append(r["conf"].unsqueeze(1))
+        confidence_map = pair_confidence
+
+    # :498-503 -- zip() stops at the V-1 source views, so only the first V-1 maps are consumed; every
+    # depth iteration appends the resized maps again (kept: callers index the list)
+    resized = [F.interpolate(confidence_map[i], [img_h, img_w], mode='bilinear', align_corners=False)
+               for i in range(n_src)]
+    weights = torch.cat(resized, 1)                                                             # [B,V-1,h,w]
+    similarity = _volume(features, proj_matrices, depth_values, sweep.AGG_WEIGHTED_PRODUCT, plane_major=True,
+                         weights=weights)                                                        # [B,D,C,h,w]
+    for d in range(num_depth):
+        pair_confidence.extend(resized)
+        reg_cost, state1, state2 = self.reg_fuse(similarity[:, d], state1, state2)               # :512
+        acc.update(d, num_depth, reg_cost, depth_values)                                         # :514-529
+    return {"depth": acc.out["depth"], "photometric_confidence": acc.out["conf"],
+            "pair_confidence": pair_confidence, "pair_result": pair_results}
+
+
+def ada_depthnet_forward(self, features, proj_matrices, depth_values, num_depth, confidence_map=None):
+    """Training-form DepthNet (adamvs.py:247-312): whole volumes, epsilon in the numerator, 3-D
+    regulariser `self.reg_fuse`, softmax + max-prob confidence."""
+    proj_matrices = torch.unbind(proj_matrices, 1)
+    _check(features, proj_matrices, depth_values, num_depth)
+    n_src = len(features) - 1
+    _, _, img_h, img_w = features[0].shape
+    pair_confidence, pair_results = [], []
+    if confidence_map is None:
+        pairs = _volume(features, proj_matrices, depth_values, sweep.AGG_PAIR_MEAN)
+        for i in range(n_src):
+            score_volume = self.reg(pairs[:, i])
+            r = _regress(score_volume, depth_values, conf_mode=sweep.CONF_MAX_PROB, want_index=False)
+            pair_results.append(r["depth"])
+            pair_confidence.append(r["conf"].unsqueeze(1))
+        weights = torch.cat(pair_confidence, 1)
+    else:
+        resized = [F.interpolate(confidence_map[i], [img_h, img_w], mode='bilinear', align_corners=False)
+                   for i in range(n_src)]
+        pair_confidence.extend(resized)
+        weights = torch.cat(resized, 1)
+    fused = _volume(features, proj_matrices, depth_values, sweep.AGG_WEIGHTED_PRODUCT, weights=weights,
+                    eps_in_numerator=True)
+    prob_volume_pre = self.reg_fuse(fused).squeeze(1)
+    r = _regress(prob_volume_pre, depth_values, conf_mode=sweep.CONF_MAX_PROB, want_index=False)
+    return {"depth": r["depth"], "photometric_confidence": r["conf"], "pair_confidence": pair_confidence,
+            "pair_result": pair_results}
+
+
+# ---------------------------------------------------------------------------------------- UCS-Net
+def ucs_compute_depth(feats, proj_mats, depth_samps, cost_reg, lamb, is_training=False):
+    proj_mats = torch.unbind(proj_mats, 1)
+    assert len(proj_mats) == len(feats), "Different number of images and projection matrices"
+    volume_variance = _volume(feats, proj_mats, depth_samps, sweep.AGG_VARIANCE)               # :119-134
+    prob_volume_pre = cost_reg(volume_variance).squeeze(1)
+    with torch.no_grad():
+        r = _regress(prob_volume_pre, depth_samps, conf_mode=sweep.CONF_WINDOW4, lamb=float(lamb))   # :137-149
+    return {"depth": r["depth"], "photometric_confidence": r["conf"], "variance": r["exp_variance"]}
+
+
+def ucs_uncertainty_samples(cur_depth, exp_var, ndepth, device, dtype, shape):
+    """ucsnet.py:30-53.  The first-stage branch is get_depth_range_samples' range branch; the
+    per-pixel branch is a handful of element-wise ops on [B,1,H,W] maps and stays in PyTorch."""
+    if cur_depth.dim() == 2:
+        from .module import get_depth_range_samples
+        return get_depth_range_samples(cur_depth, ndepth, 0.0, device, dtype, shape)
+    low_bound = cur_depth - exp_var
+    high_bound = cur_depth + exp_var
+    assert ndepth > 1
+    step = (high_bound - low_bound) / (float(ndepth) - 1)
+    return torch.cat([low_bound + step * i + 1e-12 for i in range(int(ndepth))], 1)
+
+
+# ------------------------------------------------------------------ nn.Module wrappers (parameter-free)
+class DepthNet(nn.Module):
+    """cas_mvsnet.DepthNet."""
+    forward = cas_depthnet_forward
+
+
+class REDDepthNet(nn.Module):
+    """msrednet.DepthNet."""
+    forward = red_depthnet_forward
+
+
+class REDInferDepthNet(nn.Module):
+    """msrednet.InferDepthNet."""
+    forward = red_infer_forward
+
+
+class AdaInferDepthNet(nn.Module):
+    """adamvs.InferDepthNet with the caller's regularisers: reg = CostRegNet2D(in_depths, base),
+    reg_fuse = SliceCostRegNetRED(in_channels, in_up, base) (adamvs.py:430-434)."""
+
+    def __init__(self, reg, reg_fuse, in_up=True):
+        super().__init__()
+        self.in_up = in_up
+        self.reg = reg
+        self.reg_fuse = reg_fuse
+
+    forward = ada_infer_forward

@@ -1,0 +1,214 @@
+"""Tensor-level entry points of the plane-sweep engine (one call = one libd3dsweep launch).
+
+PyTorch owns every buffer and the stream; this module only checks tensors, fills the C structs of
+`include/d3d_sweep.h` and calls the library on `torch.cuda.current_stream()`.  Inputs must be fp32
+CUDA tensors: there is no CPU path.
+
+Batch is handled above this layer (`module.py` loops over B, which is 1 in the reference's
+inference script, mvs/mvs_cas/predict.py:49).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (AGG_GROUP_CORR, AGG_PAIR_MEAN, AGG_VARIANCE, AGG_WARP, AGG_WEIGHTED_PRODUCT,  # noqa: F401
+                   CONF_MAX_PROB, CONF_WINDOW4, HYPS_PER_PIXEL, HYPS_RESIZED, HYPS_UNIFORM,
+                   SAMPLES_AROUND, SAMPLES_CASCADE, SAMPLES_RANGE, SOFTMAX_NONE, SOFTMAX_RAW_EXP,
+                   SOFTMAX_STABLE)
+
+
+def _need(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s is on %s: the sweep engine only runs on CUDA (no CPU fallback)" % (name, t.device))
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def to_texels(features, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Feature maps of all views, [V] x [C,H,W] (or one [V,C,H,W] tensor) -> channels-last [V,H,W,C]."""
+    views = list(features) if not isinstance(features, torch.Tensor) else list(features.unbind(0))
+    views = [_need(v[0] if v.dim() == 4 else v, "features[%d]" % i) for i, v in enumerate(views)]
+    c, h, w = views[0].shape
+    if out is None:
+        out = torch.empty((len(views), h, w, c), device=views[0].device, dtype=torch.float32)
+    lib = _lib.load()
+    with torch.cuda.device(views[0].device):
+        for i, v in enumerate(views):
+            if tuple(v.shape) != (c, h, w):
+                raise ValueError("features[%d] has shape %s, expected %s" % (i, tuple(v.shape), (c, h, w)))
+            _lib.check(lib.d3d_nchw_to_nhwc(v.data_ptr(), out[i].data_ptr(), c, h, w, _stream()))
+    return out
+
+
+def relative_poses(proj: torch.Tensor) -> torch.Tensor:
+    """[V,4,4] projection matrices (view 0 = reference) -> [V-1,4,4] P_src @ inverse(P_ref), computed
+    with the very ops of the reference (mvs/mvs_cas/models/module.py:528) so the matrices the kernel
+    sees are the matrices the reference sees."""
+    return torch.matmul(proj[1:], torch.inverse(proj[:1])).contiguous()
+
+
+def cost_volume(texels: torch.Tensor, pose: torch.Tensor, hyps: torch.Tensor, mode: int = AGG_VARIANCE, *,
+                groups: int = 0, weights: Optional[torch.Tensor] = None, eps_in_numerator: bool = False,
+                d_begin: int = 0, d_count: int = 0, out: Optional[torch.Tensor] = None,
+                plane_major: bool = False, variant: int = 0) -> torch.Tensor:
+    """Fused warp + aggregate.  texels [V,H,W,C]; pose [V-1,4,4]; hyps [D] or [D,H,W].
+
+    Returns [Cout, Dn, H, W] (or [Dn, Cout, H, W] with plane_major=True, the layout whose planes are
+    contiguous [Cout,H,W] slices for the plane-at-a-time regularisers), Dn = planes computed.
+    """
+    texels = _need(texels, "texels")
+    pose = _need(pose, "pose")
+    hyps = _need(hyps, "hyps")
+    v, h, w, c = texels.shape
+    if tuple(pose.shape) != (v - 1, 4, 4):
+        raise ValueError("pose must be [%d,4,4], got %s" % (v - 1, tuple(pose.shape)))
+    if hyps.dim() == 1:
+        per_pixel = 0
+    elif hyps.dim() == 3 and tuple(hyps.shape[1:]) == (h, w):
+        per_pixel = 1
+    else:
+        raise ValueError("hyps must be [D] or [D,%d,%d], got %s" % (h, w, tuple(hyps.shape)))
+    d = hyps.shape[0]
+    dn = d - d_begin if d_count <= 0 else d_count
+    if mode == AGG_GROUP_CORR:
+        cout = groups
+    elif mode == AGG_PAIR_MEAN:
+        cout = v - 1
+    else:
+        cout = c
+    if weights is not None:
+        weights = _need(weights, "weights")
+        if tuple(weights.shape) != (v - 1, h, w):
+            raise ValueError("weights must be [%d,%d,%d], got %s" % (v - 1, h, w, tuple(weights.shape)))
+    shape = (dn, cout, h, w) if plane_major else (cout, dn, h, w)
+    if out is None:
+        out = torch.empty(shape, device=texels.device, dtype=torch.float32)
+    else:
+        _need(out, "out")
+        if tuple(out.shape) != shape or not out.is_contiguous():
+            raise ValueError("out must be a contiguous %s tensor" % (shape,))
+    a = _lib.CostVolumeArgs()
+    a.struct_size = C.sizeof(a)
+    a.mode, a.num_views, a.channels, a.height, a.width, a.num_depth = mode, v, c, h, w, d
+    a.d_begin, a.d_count, a.hyps_per_pixel = d_begin, dn, per_pixel
+    a.groups, a.eps_in_numerator, a.variant = groups, int(eps_in_numerator), variant
+    a.feats, a.pose, a.hyps, a.weights, a.out = texels.data_ptr(), pose.data_ptr(), hyps.data_ptr(), _ptr(weights), out.data_ptr()
+    if plane_major:
+        a.out_stride_c, a.out_stride_d = h * w, cout * h * w
+    else:
+        a.out_stride_c, a.out_stride_d = dn * h * w, h * w
+    with torch.cuda.device(texels.device):
+        _lib.check(_lib.load().d3d_cost_volume(C.byref(a), _stream()))
+    return out
+
+
+def depth_regress(logits: torch.Tensor, hyps: torch.Tensor, *, conf_mode: int = CONF_MAX_PROB,
+                  softmax_mode: int = SOFTMAX_STABLE, num_depth: Optional[int] = None, d_begin: int = 0,
+                  state: Optional[torch.Tensor] = None, finalize: bool = True, want_index: bool = True,
+                  lamb: Optional[float] = None, next_num_depth: int = 0, next_interval: float = 0.0):
+    """Fused softmax + expectation + confidence over logits [Dn,H,W] (a strided view along D is fine).
+
+    hyps: [D] (uniform), [D,H,W] (per pixel) or [D,h',w'] (bilinearly resized to H x W, align_corners
+    False).  Returns a dict with "depth", "conf" and optionally "index", "exp_variance", "next_hyps",
+    "state".  With softmax_mode=SOFTMAX_RAW_EXP the call may cover a slice of planes starting at
+    d_begin and carries its accumulators in `state` [3,H,W].
+    """
+    if logits.dim() != 3:
+        raise ValueError("logits must be [D,H,W]")
+    if not logits.is_cuda or logits.dtype != torch.float32:
+        raise RuntimeError("logits must be an fp32 CUDA tensor (no CPU fallback)")
+    dn, h, w = logits.shape
+    if logits.stride(2) != 1 or logits.stride(1) != w:
+        logits = logits.contiguous()
+    stride_d = logits.stride(0) if dn > 1 else h * w
+    hyps = _need(hyps, "hyps")
+    d = int(num_depth) if num_depth is not None else hyps.shape[0]
+    if hyps.shape[0] != d:
+        raise ValueError("hyps has %d planes, expected %d" % (hyps.shape[0], d))
+    a = _lib.RegressArgs()
+    a.struct_size = C.sizeof(a)
+    if hyps.dim() == 1:
+        a.hyps_mode = HYPS_UNIFORM
+    elif hyps.dim() == 3 and tuple(hyps.shape[1:]) == (h, w):
+        a.hyps_mode = HYPS_PER_PIXEL
+    elif hyps.dim() == 3:
+        a.hyps_mode, a.hyps_height, a.hyps_width = HYPS_RESIZED, hyps.shape[1], hyps.shape[2]
+    else:
+        raise ValueError("hyps must be [D], [D,H,W] or [D,h,w]")
+    dev = logits.device
+    res = {}
+    raw = softmax_mode != SOFTMAX_STABLE
+    if raw and state is None and not (d_begin == 0 and dn == d):
+        raise ValueError("a RAW_EXP plane slice needs the `state` tensor")
+    if state is not None:
+        state = _need(state, "state")
+        if tuple(state.shape) != (3, h, w):
+            raise ValueError("state must be [3,%d,%d]" % (h, w))
+        res["state"] = state
+    do_final = finalize or not raw
+    if do_final:
+        res["depth"] = torch.empty((h, w), device=dev, dtype=torch.float32)
+        res["conf"] = torch.empty((h, w), device=dev, dtype=torch.float32)
+        if want_index and not raw:
+            res["index"] = torch.empty((h, w), device=dev, dtype=torch.int32)
+        if lamb is not None:
+            res["exp_variance"] = torch.empty((h, w), device=dev, dtype=torch.float32)
+        if next_num_depth > 0:
+            res["next_hyps"] = torch.empty((next_num_depth, h, w), device=dev, dtype=torch.float32)
+    a.num_depth, a.height, a.width, a.d_begin, a.d_count = d, h, w, d_begin, dn
+    a.softmax_mode, a.conf_mode, a.finalize = softmax_mode, conf_mode, int(do_final)
+    a.next_num_depth = next_num_depth if do_final else 0
+    a.next_interval = float(next_interval)
+    a.lamb = float(lamb) if lamb is not None else 0.0
+    a.logits, a.logits_stride_d, a.hyps = logits.data_ptr(), stride_d, hyps.data_ptr()
+    a.depth, a.conf, a.index = _ptr(res.get("depth")), _ptr(res.get("conf")), _ptr(res.get("index"))
+    a.state, a.exp_variance, a.next_hyps = _ptr(state), _ptr(res.get("exp_variance")), _ptr(res.get("next_hyps"))
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().d3d_depth_regress(C.byref(a), _stream()))
+    return res
+
+
+def depth_samples(mode: int, num_depth: int, hw: Tuple[int, int], *, device=None, cur: Optional[torch.Tensor] = None,
+                  interval: float = 0.0, dmin: float = 0.0, dmax: float = 0.0,
+                  full_hw: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """Depth hypotheses [D,H,W] for a stage (include/d3d_sweep.h: D3D_SAMPLES_*)."""
+    h, w = int(hw[0]), int(hw[1])
+    if cur is not None:
+        cur = _need(cur, "cur")
+        device = cur.device
+    if device is None:
+        raise ValueError("device is required when cur is None")
+    out = torch.empty((num_depth, h, w), device=device, dtype=torch.float32)
+    a = _lib.SamplesArgs()
+    a.struct_size = C.sizeof(a)
+    a.mode, a.num_depth, a.height, a.width = mode, num_depth, h, w
+    if cur is not None:
+        if cur.dim() != 2:
+            raise ValueError("cur must be [h,w]")
+        a.src_height, a.src_width = cur.shape
+        if mode == SAMPLES_AROUND and tuple(cur.shape) != (h, w):
+            raise ValueError("cur must be [%d,%d] for SAMPLES_AROUND" % (h, w))
+    if full_hw is not None:
+        a.full_height, a.full_width = int(full_hw[0]), int(full_hw[1])
+    else:
+        a.full_height, a.full_width = h, w
+    a.interval, a.dmin, a.dmax = float(interval), float(dmin), float(dmax)
+    a.cur, a.out = _ptr(cur), out.data_ptr()
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.load().d3d_depth_samples(C.byref(a), _stream()))
+    return out

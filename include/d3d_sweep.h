@@ -1,0 +1,174 @@
+/*
+ * d3d_sweep.h -- C ABI of libd3dsweep.so, the sm_100a plane-sweep cost-volume engine.
+ *
+ * The reference (gpcv-liujin/Deep3D_Aerial) has no FFI layer: its hot path is a set of Python
+ * functions under mvs/mvs_cas/models/ that call ATen ops.  Every entry point below therefore
+ * cites the reference *Python* interface it stands in for; the Python shim that re-exports those
+ * names lives in deep3d_aerial_b200/ (module.py, cas_mvsnet.py, adamvs.py, msrednet.py, ucsnet.py)
+ * and INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device; the library never allocates,
+ *     frees or keeps caller memory;
+ *   - work is enqueued on the caller's stream (a cudaStream_t passed as void*) and the call
+ *     returns without synchronising; it is safe under CUDA-graph capture;
+ *   - return value 0 = success, otherwise a D3D_ERR_* code and d3d_last_error() (thread local)
+ *     describes it; nothing is launched on error;
+ *   - all floating point data is fp32; image extents are rows x cols = height x width;
+ *   - batch is handled by the caller (one call per batch item; the reference runs B = 1,
+ *     mvs/mvs_cas/predict.py:49).
+ *   - structs start with struct_size = sizeof(struct) so fields can be appended compatibly.
+ */
+#ifndef D3D_SWEEP_H_
+#define D3D_SWEEP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D3D_VERSION 100 /* 0.1.0 */
+
+enum {
+    D3D_OK = 0,
+    D3D_ERR_BAD_ARGUMENT = 1, /* null pointer, non-positive extent, unknown enum, bad struct_size */
+    D3D_ERR_UNSUPPORTED = 2,  /* shape outside what the kernels are instantiated for            */
+    D3D_ERR_CUDA = 3          /* a CUDA runtime call failed; message holds cudaGetErrorString     */
+};
+
+/* How the per-view warped features are aggregated into the cost volume. */
+enum {
+    /* out[C,D,H,W] = the warped source view itself (num_views must be 2).
+     * Replaces homo_warping_float, mvs/mvs_cas/models/module.py:516-557. */
+    D3D_AGG_WARP = 0,
+    /* out[C,D,H,W] = sq/V - (sum/V)^2 over the reference and the V-1 warped views.
+     * Replaces cas_mvsnet.py:46-60, msrednet.py:217-230 and 401-414, ucsnet.py:119-134. */
+    D3D_AGG_VARIANCE = 1,
+    /* out[G,D,H,W] = mean over source views of mean_{C/G}(ref * warped).
+     * Stands in for the commented-out groupwise_correlation(ref, warped, 8, 1) at
+     * adamvs.py:271,295 (body not in the reference; defined by analogy with adamvs.py:473). */
+    D3D_AGG_GROUP_CORR = 2,
+    /* out[C,D,H,W] = sum_i (warped_i*ref)*w_i / (1e-5 + sum_i w_i)      (adamvs.py:492-509), or with
+     * eps_in_numerator: (1e-5 + sum_i (warped_i*ref)*w_i) / sum_i w_i   (adamvs.py:262,287-301). */
+    D3D_AGG_WEIGHTED_PRODUCT = 3,
+    /* out[V-1,D,H,W]: out[i] = mean_C(ref * warped_i)                   (adamvs.py:466-475). */
+    D3D_AGG_PAIR_MEAN = 4
+};
+
+typedef struct D3dCostVolumeArgs {
+    uint32_t struct_size;
+    int32_t mode;             /* D3D_AGG_*                                                        */
+    int32_t num_views;        /* V: reference + V-1 sources, 2 <= V <= 9                          */
+    int32_t channels;         /* C: multiple of 4; C/4 or C/8 must be a power of two <= 32        */
+    int32_t height, width;    /* feature-map rows, cols                                           */
+    int32_t num_depth;        /* D: planes in `hyps`                                              */
+    int32_t d_begin, d_count; /* planes [d_begin, d_begin+d_count) are computed (slice mode for
+                                 the plane-at-a-time GRU regularisers, adamvs.py:492, msrednet.py:400);
+                                 d_count <= 0 means "through the last plane"                      */
+    int32_t hyps_per_pixel;   /* 0: hyps[D] (fronto-parallel sweep); 1: hyps[D,H,W]               */
+    int32_t groups;           /* G for D3D_AGG_GROUP_CORR (C % G == 0)                            */
+    int32_t eps_in_numerator; /* D3D_AGG_WEIGHTED_PRODUCT: training-form epsilon placement        */
+    int32_t variant;          /* 0 = production kernel; others select A/B kernels */
+    int32_t reserved0;
+    const float* feats;       /* [V,H,W,C] channels-last, view 0 = reference (d3d_nchw_to_nhwc)   */
+    const float* pose;        /* [V-1,4,4] row-major P_src @ inverse(P_ref), module.py:528-530    */
+    const float* hyps;        /* depth hypotheses, see hyps_per_pixel                             */
+    const float* weights;     /* [V-1,H,W] view weights (WEIGHTED_PRODUCT only), already at H x W  */
+    float* out;               /* plane d of channel c at out[c*out_stride_c + (d-d_begin)*out_stride_d
+                                 + y*W + x]                                                       */
+    int64_t out_stride_c;     /* elements; 0 selects the dense [Cout, d_count, H, W] layout        */
+    int64_t out_stride_d;     /* elements; 0 selects H*W                                          */
+} D3dCostVolumeArgs;
+
+/* Fused homography warp + bilinear sample + aggregation; the V x C x D x H x W warped volume is
+ * never materialised. */
+int d3d_cost_volume(const D3dCostVolumeArgs* args, void* cuda_stream);
+
+enum { D3D_SOFTMAX_STABLE = 0, /* p = softmax_D(logit)  (F.softmax, cas_mvsnet.py:69)               */
+       D3D_SOFTMAX_RAW_EXP = 1,/* un-normalised exp(logit), no max subtraction, streaming
+                                  accumulators (adamvs.py:514-529, msrednet.py:418-437)             */
+       D3D_SOFTMAX_NONE = 2    /* input already is a probability volume: depth = sum p*d, conf =
+                                  max p, no normalisation (depth_regression, module.py:605-613)     */ };
+enum { D3D_CONF_MAX_PROB = 0,  /* conf = max_d p, index = argmax (msrednet.py:238, adamvs.py:310)   */
+       D3D_CONF_WINDOW4 = 1    /* i = clamp(floor(sum p*k)); conf = p[i-1]+p[i]+p[i+1]+p[i+2]
+                                  (cas_mvsnet.py:72-76, ucsnet.py:140-146)                          */ };
+enum { D3D_HYPS_UNIFORM = 0,   /* hyps[D]                                                           */
+       D3D_HYPS_PER_PIXEL = 1, /* hyps[D,H,W]                                                       */
+       D3D_HYPS_RESIZED = 2    /* hyps[D,hyps_height,hyps_width] bilinearly resized to H x W with
+                                  align_corners=False (module.py:608-610, adamvs.py:519-520)        */ };
+
+typedef struct D3dRegressArgs {
+    uint32_t struct_size;
+    int32_t num_depth;        /* D: planes of the whole sweep                                     */
+    int32_t height, width;    /* rows, cols of the logit maps                                     */
+    int32_t d_begin, d_count; /* `logits` holds planes [d_begin, d_begin+d_count); d_count <= 0:
+                                 all D.  Slices need D3D_SOFTMAX_RAW_EXP or _NONE                 */
+    int32_t softmax_mode;     /* D3D_SOFTMAX_*                                                    */
+    int32_t conf_mode;        /* D3D_CONF_* (RAW_EXP implies MAX_PROB)                            */
+    int32_t hyps_mode;        /* D3D_HYPS_*                                                       */
+    int32_t hyps_height, hyps_width; /* D3D_HYPS_RESIZED only                                     */
+    int32_t finalize;         /* RAW_EXP/NONE: 1 = also write depth and conf (RAW_EXP: acc/(sum+1e-10)) */
+    int32_t next_num_depth;   /* > 0: also emit next-stage hypotheses (module.py:616-630)         */
+    float lamb;               /* exp_variance scale (ucsnet.py:148-149)                           */
+    int32_t reserved0;
+    double next_interval;     /* depth_inteval_pixel of the next stage (a Python float upstream)  */
+    const float* logits;      /* [d_count,H,W], plane stride logits_stride_d                      */
+    int64_t logits_stride_d;  /* elements; 0 selects H*W                                          */
+    const float* hyps;        /* all D planes (indexed with d_begin+k), layout per hyps_mode      */
+    float* depth;             /* [H,W] expected depth (module.py:605-613); may be NULL if !finalize */
+    float* conf;              /* [H,W] photometric confidence                                     */
+    int32_t* index;           /* [H,W] argmax plane (MAX_PROB) or window base i (WINDOW4); NULL ok */
+    float* state;             /* RAW_EXP: [3,H,W] = exp_sum, depth_sum, max_prob; read unless
+                                 d_begin == 0, always written.  NULL allowed when the call covers
+                                 all D planes                                                      */
+    float* exp_variance;      /* [H,W] lamb*sqrt(sum p (d-depth)^2), STABLE only; NULL = skip     */
+    float* next_hyps;         /* [next_num_depth,H,W]: depth -/+ next_num_depth/2*next_interval   */
+} D3dRegressArgs;
+
+/* Fused softmax over D + expected depth + confidence (+ argmax, + UCS-Net spread, + next-stage
+ * hypotheses).  One pass over the logits. */
+int d3d_depth_regress(const D3dRegressArgs* args, void* cuda_stream);
+
+enum { D3D_SAMPLES_RANGE = 0,     /* [dmin,dmax] -> linspace planes broadcast to [D,H,W]
+                                     (module.py:637-645)                                          */
+       D3D_SAMPLES_AROUND = 1,    /* cur[H,W] -> cur -/+ D/2*interval, D planes (module.py:616-630) */
+       D3D_SAMPLES_CASCADE = 2    /* Cas-MVSNet / RED-Net stage glue (cas_mvsnet.py:206-226,
+                                     msrednet.py:495-515): cur[src_h,src_w] (or the range) bilinear
+                                     -> full res, samples at full res, trilinear -> [D,H,W]        */ };
+
+typedef struct D3dSamplesArgs {
+    uint32_t struct_size;
+    int32_t mode;              /* D3D_SAMPLES_*                                                    */
+    int32_t num_depth;         /* D of the stage being prepared                                    */
+    int32_t height, width;     /* output rows, cols                                                */
+    int32_t src_height, src_width; /* extent of `cur` (CASCADE); ignored otherwise                 */
+    int32_t full_height, full_width; /* CASCADE: full-resolution extent                            */
+    float dmin, dmax;          /* RANGE, and CASCADE when cur == NULL                              */
+    int32_t reserved0;
+    double interval;           /* depth_inteval_pixel = ratio * (dmax-dmin)/num_depth_total        */
+    const float* cur;          /* previous depth estimate; NULL with CASCADE = first stage (range) */
+    float* out;                /* [D,H,W]                                                          */
+} D3dSamplesArgs;
+
+/* Per-stage depth-hypothesis resampling, get_depth_range_samples (module.py:633-650). */
+int d3d_depth_samples(const D3dSamplesArgs* args, void* cuda_stream);
+
+/* Feature relayout [C,H,W] -> [H,W,C] (the sweep kernel gathers whole texels). */
+int d3d_nchw_to_nhwc(const float* in, float* out, int32_t channels, int32_t height, int32_t width,
+                     void* cuda_stream);
+
+/* Thread-local description of the last error returned on this thread ("" if none). */
+const char* d3d_last_error(void);
+int d3d_version(void);
+/* Number of kernels this library has launched in the calling process (bench accounting). */
+int64_t d3d_launch_count(void);
+/* sizeof() of an argument struct as compiled into the library: 0 = D3dCostVolumeArgs,
+ * 1 = D3dRegressArgs, 2 = D3dSamplesArgs; -1 for anything else.  Lets a binding check its layout
+ * without a GPU. */
+int32_t d3d_abi_sizeof(int32_t which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D3D_SWEEP_H_ */

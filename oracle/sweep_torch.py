@@ -264,16 +264,17 @@ def uncertainty_samples(cur_depth, spread, ndepth):
 
 
 # ------------------------------------------------------------- timed CPU baseline
-def cpu_step_variance(features, proj_matrices, depth_values, plane_chunk=None):
+def cpu_step_variance(features, proj_matrices, depth_values, logits, plane_chunk=None):
     """One pass of the hot path the way the reference runs it on CPU: variance volume
-    (depth-sliced like `msrednet.py:400-414` when plane_chunk is given, so temporaries fit),
-    then softmax + regression + max-prob confidence on a stand-in logit volume
-    (-mean_C variance; the CNN regulariser is out of scope on both arms)."""
+    (depth-sliced like `msrednet.py:400-414` when plane_chunk is given, so temporaries fit), then
+    softmax + regression + max-prob confidence on the given logit volume [B,D,H,W] (the CNN
+    regulariser between the two is out of scope on both arms, so the logits are an input).
+    Returns (depth, conf, checksum of the variance volume)."""
     d_total = depth_values.shape[1]
     step = plane_chunk or d_total
-    logits = []
+    check = 0.0
     for d0 in range(0, d_total, step):
         var = variance_volume(features, proj_matrices, depth_values[:, d0:d0 + step])
-        logits.append(-var.mean(1))
-    logits = torch.cat(logits, 1)
-    return regress_maxprob(logits, depth_values)
+        check += float(var[..., ::7, ::5].sum())
+    depth, conf, _ = regress_maxprob(logits, depth_values)
+    return depth, conf, check

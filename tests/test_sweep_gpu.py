@@ -1,0 +1,382 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes -> libd3dsweep.so), against
+  (1) the committed golden vectors produced by the live reference (tests/golden, oracle/make_golden.py),
+  (2) the oracle (oracle/sweep_torch.py) on the same seeded synthetic inputs, on CPU-ATen and on
+      CUDA-ATen (the reference's own path on this GPU),
+  (3) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances are north_star's: cost volumes <= 1e-4 relative (norm-wise: max|a-b| / max|b|, SURVEY.md §7
+hard part 2), regressed depth <= 1e-3 relative, arg-max plane agreement >= 99.9 %.
+"""
+import pytest
+import torch
+
+from conftest import load_golden, rel_norm_err
+from deep3d_aerial_b200 import depthnets, module, sweep, synth
+from oracle import standins, sweep_torch
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+VOL_TOL = 1e-4     # cost volume, norm-wise relative
+DEPTH_TOL = 1e-3   # regressed depth, relative
+DEV = "cuda"
+
+
+def _views(feats):
+    return [feats[i:i + 1] for i in range(feats.shape[0])]
+
+
+def _cuda_views(feats):
+    return [f.to(DEV) for f in _views(feats)]
+
+
+def _depth_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float(((a - b).abs() / b.abs().clamp_min(1e-12)).max())
+
+
+def _scene(v, c, d, h, w, seed=0, smooth=False, perpixel=False, rig=None, scale=4):
+    rig = rig or synth.tiny_rig(num_views=v, width=w * scale, height=h * scale)
+    proj = torch.from_numpy(rig.proj(scale)).unsqueeze(0)
+    feats = synth.make_features(v, c, h, w, seed=seed, smooth=smooth)
+    if perpixel:
+        cur = synth.smooth_depth_map(rig, h, w, seed=seed)
+        hyps = synth.per_pixel_hypotheses(cur, d, (rig.dmax - rig.dmin) / (4 * d)).unsqueeze(0)
+    else:
+        hyps = synth.uniform_hypotheses(rig.dmin, rig.dmax, d).unsqueeze(0)
+    return rig, proj, feats, hyps
+
+
+def _ours_volume(feats, proj, hyps, mode, **kw):
+    """feats [V,C,H,W] cpu, proj [1,V,4,4], hyps [1,D] or [1,D,H,W] -> volume on cpu."""
+    tex = sweep.to_texels(feats.to(DEV))
+    pose = sweep.relative_poses(proj[0].to(DEV))
+    return sweep.cost_volume(tex, pose, hyps[0].to(DEV).contiguous(), mode, **kw).cpu()
+
+
+# ------------------------------------------------------------------ (1) golden vectors of the live reference
+@pytest.mark.parametrize("name", ["warp_uniform", "warp_perpixel", "warp_oob"])
+def test_homo_warping_matches_golden(name):
+    g = load_golden(name)
+    v = g["feats"].shape[0]
+    for i in range(1, v):
+        got = module.homo_warping_float(g["feats"][i:i + 1].to(DEV), g["proj"][:, i].to(DEV), g["proj"][:, 0].to(DEV),
+                                        g["hyps"].to(DEV))
+        assert got.shape == g["warped"][:, i - 1].shape
+        assert rel_norm_err(got, g["warped"][:, i - 1]) < VOL_TOL
+
+
+@pytest.mark.parametrize("name", ["cas_depthnet_uniform", "cas_depthnet_perpixel"])
+def test_cas_depthnet_matches_golden(name):
+    g = load_golden(name)
+    cap = standins.Capture(standins.reg3d)
+    out = depthnets.DepthNet()(_cuda_views(g["feats"]), g["proj"].to(DEV), g["hyps"].to(DEV), g["hyps"].shape[1], cap)
+    assert rel_norm_err(cap.seen[0], g["variance"]) < VOL_TOL
+    assert _depth_err(out["depth"], g["depth"]) < DEPTH_TOL
+    # same logits on both sides -> confidence must agree too (window index may flip on a knife edge)
+    ref_logits = standins.reg3d(g["variance"]).squeeze(1)[0].to(DEV)
+    r = sweep.depth_regress(ref_logits, g["hyps"][0].to(DEV).contiguous(), conf_mode=sweep.CONF_WINDOW4)
+    assert _depth_err(r["depth"], g["depth"][0]) < DEPTH_TOL
+    close = (r["conf"].cpu() - g["conf"][0]).abs() < 1e-4
+    assert close.float().mean() >= 0.999
+
+
+def test_red_infer_matches_golden():
+    g = load_golden("red_infer_depthnet")
+    cap = standins.Capture(standins.slice_reg_red)
+    out = depthnets.REDInferDepthNet()(_cuda_views(g["feats"]), g["proj"].to(DEV), g["hyps"].to(DEV),
+                                       g["hyps"].shape[1], cap)
+    got = torch.stack(cap.seen, 2)            # [B,C,D,H,W]
+    assert rel_norm_err(got, g["variance_slices"]) < VOL_TOL
+    assert _depth_err(out["depth"], g["depth"]) < DEPTH_TOL
+    assert rel_norm_err(out["photometric_confidence"], g["conf"]) < 1e-3
+
+
+class _Ada:
+    """Stands where the reference's adamvs.InferDepthNet instance would (self.reg / self.reg_fuse / in_up)."""
+
+    def __init__(self, in_up):
+        self.in_up = in_up
+        self.reg = standins.reg2d_pair
+        self.fuse = standins.Capture(standins.slice_reg_up if in_up else standins.slice_reg_same)
+        self.reg_fuse = self.fuse
+
+
+def test_adamvs_infer_matches_golden():
+    g = load_golden("ada_infer_depthnet")
+    d = g["hyps"].shape[1]
+    net = _Ada(in_up=True)
+    out = depthnets.ada_infer_forward(net, _cuda_views(g["feats"]), g["proj"].to(DEV), g["hyps"].to(DEV), d)
+    assert rel_norm_err(torch.stack(out["pair_result"], 1), g["pair_result"]) < DEPTH_TOL
+    assert rel_norm_err(torch.stack(out["pair_confidence"][:3], 1), g["pair_conf_head"]) < 1e-3
+    assert len(out["pair_confidence"]) == g["n_pair_confidence"]          # the reference's list quirk
+    assert rel_norm_err(torch.stack(net.fuse.seen, 2), g["similarity_slices"]) < VOL_TOL
+    assert _depth_err(out["depth"], g["depth"]) < DEPTH_TOL
+    assert rel_norm_err(out["photometric_confidence"], g["conf"]) < 1e-3
+    pairs = _ours_volume(g["feats"], g["proj"], g["hyps"], sweep.AGG_PAIR_MEAN)
+    assert rel_norm_err(pairs, g["pair_volumes"][0]) < VOL_TOL
+    # stage 2 consumes the first V-1 maps of the over-long list, resized again
+    d2 = g["hyps2"].shape[1]
+    net2 = _Ada(in_up=False)
+    out2 = depthnets.ada_infer_forward(net2, _cuda_views(g["feats2"]), g["proj2"].to(DEV), g["hyps2"].to(DEV), d2,
+                                       confidence_map=out["pair_confidence"])
+    assert rel_norm_err(torch.stack(net2.fuse.seen, 2), g["similarity_slices2"]) < VOL_TOL
+    assert _depth_err(out2["depth"], g["depth2"]) < DEPTH_TOL
+    assert rel_norm_err(out2["photometric_confidence"], g["conf2"]) < 1e-3
+    assert len(out2["pair_confidence"]) == g["n_pair_confidence2"]
+
+
+def test_adamvs_train_form_matches_golden():
+    g = load_golden("ada_train_depthnet")
+    w = g["pair_conf"][0, :, 0].to(DEV).contiguous()             # [V-1,h,w]
+    fused = _ours_volume(g["feats"], g["proj"], g["hyps"], sweep.AGG_WEIGHTED_PRODUCT, weights=w, eps_in_numerator=True)
+    assert rel_norm_err(fused, g["fused"][0]) < VOL_TOL
+    r = sweep.depth_regress((-3.0 * g["fused"].mean(1))[0].to(DEV), g["hyps"][0].to(DEV).contiguous())
+    assert _depth_err(r["depth"], g["depth"][0]) < DEPTH_TOL
+    assert rel_norm_err(r["conf"], g["conf"][0]) < 1e-3
+
+
+def test_regression_and_samples_match_golden():
+    g = load_golden("regress_misc")
+    prob = torch.softmax(g["logits"], 1)
+    got = module.depth_regression(prob.to(DEV), g["hy_small"].to(DEV))          # resized 4-D hypotheses
+    assert _depth_err(got, g["depth_resized"]) < 1e-5
+    rng = torch.tensor([[400.0, 600.0]], device=DEV)
+    got = module.get_depth_range_samples(rng, 10, 0.0, DEV, torch.float32, [1, 12, 16])
+    assert torch.equal(got.cpu(), g["samples_range"])
+    got = module.get_depth_range_samples(g["cur"].to(DEV), 8, 0.52, DEV, torch.float32, [1, 12, 16])
+    assert torch.equal(got.cpu(), g["samples_cur"])
+
+
+def test_cascade_stage_glue_matches_golden():
+    g = load_golden("cas_stage_glue")
+    fh, fw = [int(x) for x in g["full_hw"]]
+    interval = (g["dmax"] - g["dmin"]) / g["num_depth"]
+    nd = [int(x) for x in g["ndepths"]]
+    ratios = [int(x) for x in g["ratios"]]
+    dv1 = sweep.depth_samples(sweep.SAMPLES_CASCADE, nd[0], (fh // 4, fw // 4), device=DEV, dmin=g["dmin"],
+                              dmax=g["dmax"], full_hw=(fh, fw))
+    assert rel_norm_err(dv1, g["dv1"][0]) < 1e-6
+    dv2 = sweep.depth_samples(sweep.SAMPLES_CASCADE, nd[1], (fh // 2, fw // 2), cur=g["depth1"][0].to(DEV),
+                              interval=ratios[1] * interval, full_hw=(fh, fw))
+    assert rel_norm_err(dv2, g["dv2"][0]) < 1e-6
+    dv3 = sweep.depth_samples(sweep.SAMPLES_CASCADE, nd[2], (fh, fw), cur=g["depth2"][0].to(DEV),
+                              interval=ratios[2] * interval, full_hw=(fh, fw))
+    assert rel_norm_err(dv3, g["dv3"][0]) < 1e-6
+
+
+def test_ucs_compute_depth_matches_golden():
+    g = load_golden("ucs_compute_depth")
+    out = depthnets.ucs_compute_depth(_cuda_views(g["feats"]), g["proj"].to(DEV), g["hyps"].to(DEV), standins.reg3d, 1.5)
+    assert _depth_err(out["depth"], g["depth"]) < DEPTH_TOL
+    assert rel_norm_err(out["variance"], g["exp_variance"]) < 2e-3
+    var = _ours_volume(g["feats"], g["proj"], g["hyps"], sweep.AGG_VARIANCE)
+    assert rel_norm_err(var, g["variance"][0]) < VOL_TOL
+
+
+# ------------------------------------------------------------------ (2) oracle on seeded synthetic inputs
+CASES = [  # v, c, d, h, w, perpixel
+    (3, 8, 48, 128, 160, False),     # BASELINE.json config 1
+    (5, 32, 24, 86, 58, False),      # config-2 shaped (1/8 linear size), 4 lanes x 8 channels per pixel
+    (5, 32, 16, 86, 58, True),
+    (5, 16, 12, 77, 45, True),       # cascade stage 2 shape class, ragged tile tail
+    (5, 8, 8, 90, 61, True),         # cascade stage 3 shape class
+    (2, 4, 6, 33, 47, False),        # one source view, 4 channels
+    (7, 32, 10, 40, 36, False),      # 6 source views -> 4 channels per lane
+    (9, 16, 6, 24, 28, True),        # 8 source views (the maximum)
+    (3, 64, 6, 20, 24, False),       # 64 channels
+]
+
+
+@pytest.mark.parametrize("v,c,d,h,w,perpixel", CASES)
+@pytest.mark.parametrize("oracle_dev", ["cpu", "cuda"])
+def test_variance_matches_oracle(v, c, d, h, w, perpixel, oracle_dev):
+    _, proj, feats, hyps = _scene(v, c, d, h, w, seed=3, perpixel=perpixel)
+    want = sweep_torch.variance_volume([f.to(oracle_dev) for f in _views(feats)], proj.to(oracle_dev),
+                                       hyps.to(oracle_dev))[0]
+    got = _ours_volume(feats, proj, hyps, sweep.AGG_VARIANCE)
+    assert got.shape == want.shape
+    assert rel_norm_err(got, want) < VOL_TOL
+
+
+@pytest.mark.parametrize("smooth", [False, True])
+def test_whu_shaped_rig_matches_oracle(smooth):
+    """The WHU-OMVS cross rig of SURVEY.md §8d (f=4000 at 1856x2752, 40 m baselines, 400-600 m) on a crop-sized
+    feature map: coordinates of the production magnitude, so fp32 rounding of the projection matters."""
+    rig = synth.make_rig(num_views=5)
+    h, w, d, c = 172, 116, 12, 32          # 1/16 of full res: scale 16 keeps the full-size geometry
+    _, proj, feats, hyps = _scene(5, c, d, h, w, seed=5, smooth=smooth, rig=rig, scale=16)
+    want = sweep_torch.variance_volume(_cuda_views(feats), proj.to(DEV), hyps.to(DEV))[0]
+    got = _ours_volume(feats, proj, hyps, sweep.AGG_VARIANCE)
+    assert rel_norm_err(got, want) < VOL_TOL
+
+
+@pytest.mark.parametrize("groups", [1, 4, 8, 32])
+def test_group_corr_matches_oracle(groups):
+    _, proj, feats, hyps = _scene(5, 32, 10, 40, 52, seed=4)
+    want = sweep_torch.groupwise_correlation_volume(_views(feats), proj, hyps, groups)[0]
+    got = _ours_volume(feats, proj, hyps, sweep.AGG_GROUP_CORR, groups=groups)
+    assert got.shape == want.shape
+    assert rel_norm_err(got, want) < VOL_TOL
+
+
+def test_group_corr_wide_groups_lane_reduction():
+    _, proj, feats, hyps = _scene(7, 32, 6, 20, 28, seed=6)      # 4 channels per lane, groups of 16 span 4 lanes
+    want = sweep_torch.groupwise_correlation_volume(_views(feats), proj, hyps, 2)[0]
+    got = _ours_volume(feats, proj, hyps, sweep.AGG_GROUP_CORR, groups=2)
+    assert rel_norm_err(got, want) < VOL_TOL
+
+
+@pytest.mark.parametrize("eps_num", [False, True])
+def test_weighted_product_matches_oracle(eps_num):
+    v, c, d, h, w = 5, 16, 8, 36, 44
+    _, proj, feats, hyps = _scene(v, c, d, h, w, seed=7, perpixel=True)
+    g = torch.Generator().manual_seed(1)
+    weights = [torch.rand(1, 1, h // 2, w // 2, generator=g) for _ in range(v - 1)]
+    want = sweep_torch.weighted_product_volume(_views(feats), proj, hyps, weights, eps_in_numerator=eps_num)[0]
+    wt = torch.cat([sweep_torch.resize_weight(x, h, w) for x in weights], 1)[0].to(DEV).contiguous()
+    got = _ours_volume(feats, proj, hyps, sweep.AGG_WEIGHTED_PRODUCT, weights=wt, eps_in_numerator=eps_num)
+    assert rel_norm_err(got, want) < VOL_TOL
+
+
+def test_pair_mean_matches_oracle():
+    _, proj, feats, hyps = _scene(5, 32, 12, 43, 29, seed=8)
+    hy4 = hyps.view(1, -1, 1, 1).repeat(1, 1, 43, 29)
+    want = torch.stack(sweep_torch.pair_mean_volumes(_views(feats), proj, hy4), 1)[0]
+    got = _ours_volume(feats, proj, hy4, sweep.AGG_PAIR_MEAN)
+    assert rel_norm_err(got, want) < VOL_TOL
+
+
+def test_plane_slices_and_plane_major_layout():
+    _, proj, feats, hyps = _scene(3, 8, 12, 40, 48, seed=9)
+    full = _ours_volume(feats, proj, hyps, sweep.AGG_VARIANCE)
+    part = _ours_volume(feats, proj, hyps, sweep.AGG_VARIANCE, d_begin=5, d_count=4)
+    assert torch.equal(part, full[:, 5:9])
+    pm = _ours_volume(feats, proj, hyps, sweep.AGG_VARIANCE, plane_major=True)
+    assert torch.equal(pm.permute(1, 0, 2, 3), full)
+    one = _ours_volume(feats, proj, hyps[:, 3:4], sweep.AGG_VARIANCE)           # D = 1
+    assert torch.equal(one, full[:, 3:4])
+
+
+def test_points_behind_the_camera_contribute_zero():
+    """z <= 0 is unguarded upstream (module.py:542 divides by it); here such samples are defined to be
+    out of bounds, so the volume stays finite (SURVEY.md §7 hard part 6)."""
+    _, proj, feats, hyps = _scene(3, 8, 6, 24, 32, seed=10)
+    hyps = hyps.clone()
+    hyps[0, 0] = -5.0
+    hyps[0, 1] = 0.0
+    got = _ours_volume(feats, proj, hyps, sweep.AGG_VARIANCE)
+    assert torch.isfinite(got).all()
+    want = sweep_torch.variance_volume(_views(feats), proj, hyps[:, 2:])[0]
+    assert rel_norm_err(got[:, 2:], want) < VOL_TOL
+
+
+# kernel 2 ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,h,w", [(48, 64, 80), (384, 43, 29), (8, 30, 50), (5, 7, 9)])
+@pytest.mark.parametrize("conf", ["max", "win4"])
+def test_softmax_regression_matches_oracle(d, h, w, conf):
+    logits = synth.planted_logits(d, h, w, seed=d)
+    hyps = synth.uniform_hypotheses(400.0, 600.0, d)
+    fn = sweep_torch.regress_maxprob if conf == "max" else sweep_torch.regress_window4
+    depth, cf, idx = fn(logits.unsqueeze(0), hyps.unsqueeze(0))
+    mode = sweep.CONF_MAX_PROB if conf == "max" else sweep.CONF_WINDOW4
+    r = sweep.depth_regress(logits.to(DEV), hyps.to(DEV), conf_mode=mode)
+    assert _depth_err(r["depth"], depth[0]) < DEPTH_TOL
+    agree = (r["index"].cpu().long() == idx[0]).float().mean()
+    assert agree >= 0.999
+    same = r["index"].cpu().long() == idx[0]
+    assert ((r["conf"].cpu() - cf[0]).abs()[same] < 1e-5).all()
+
+
+def test_softmax_regression_per_pixel_hypotheses_and_next_stage():
+    d, h, w = 32, 40, 56
+    rig = synth.make_rig()
+    logits = synth.planted_logits(d, h, w, seed=2)
+    hyps = synth.per_pixel_hypotheses(synth.smooth_depth_map(rig, h, w), d, 1.04)
+    depth, cf, idx = sweep_torch.regress_maxprob(logits.unsqueeze(0), hyps.unsqueeze(0))
+    r = sweep.depth_regress(logits.to(DEV), hyps.to(DEV), next_num_depth=8, next_interval=0.52)
+    assert _depth_err(r["depth"], depth[0]) < DEPTH_TOL
+    want_next = sweep_torch.depth_range_samples(r["depth"].cpu().unsqueeze(0), 8, 0.52, [1, h, w])[0]
+    assert torch.equal(r["next_hyps"].cpu(), want_next)
+
+
+def test_streaming_raw_exp_matches_oracle_slice_by_slice():
+    d, h, w = 12, 20, 28
+    logits = 0.5 * synth.planted_logits(d, 2 * h, 2 * w, seed=4)           # adamvs stage 1: logits at 2x
+    hyps = synth.per_pixel_hypotheses(synth.smooth_depth_map(synth.make_rig(), h, w), d, 4.0)
+    want_d, want_c = sweep_torch.regress_streaming([logits[k].view(1, 1, 2 * h, 2 * w) for k in range(d)],
+                                                   [hyps[k].view(1, 1, h, w) for k in range(d)], upsample2=True)
+    state = torch.zeros(3, 2 * h, 2 * w, device=DEV)
+    lg = logits.to(DEV)
+    hy = hyps.to(DEV)
+    for k in range(d):
+        r = sweep.depth_regress(lg[k:k + 1], hy, softmax_mode=sweep.SOFTMAX_RAW_EXP, d_begin=k, state=state,
+                                finalize=(k == d - 1))
+    assert _depth_err(r["depth"], want_d[0]) < DEPTH_TOL
+    assert rel_norm_err(r["conf"], want_c[0]) < 1e-4
+    whole = sweep.depth_regress(lg, hy, softmax_mode=sweep.SOFTMAX_RAW_EXP)
+    assert _depth_err(whole["depth"], want_d[0]) < DEPTH_TOL
+
+
+def test_exp_variance_matches_oracle():
+    d, h, w = 8, 24, 24
+    logits = synth.planted_logits(d, h, w, seed=6) * 0.3
+    hyps = synth.per_pixel_hypotheses(synth.smooth_depth_map(synth.make_rig(), h, w), d, 2.0)
+    prob = torch.softmax(logits, 0).unsqueeze(0)
+    depth = sweep_torch.expectation(prob, hyps.unsqueeze(0))
+    want = sweep_torch.exp_variance(prob, hyps.unsqueeze(0), depth, 1.5)
+    r = sweep.depth_regress(logits.to(DEV), hyps.to(DEV), conf_mode=sweep.CONF_WINDOW4, lamb=1.5)
+    assert rel_norm_err(r["exp_variance"], want[0]) < 1e-3
+
+
+def test_texel_relayout_round_trip():
+    f = synth.make_features(3, 16, 37, 53, seed=1)
+    tex = sweep.to_texels(f.to(DEV))
+    assert torch.equal(tex.cpu(), f.permute(0, 2, 3, 1).contiguous())
+
+
+# ------------------------------------------------------------------ (3) properties at full size
+@pytest.mark.parametrize("mode,kw", [(sweep.AGG_VARIANCE, {}), (sweep.AGG_GROUP_CORR, {"groups": 8})])
+def test_full_size_config_against_cuda_aten_on_plane_subsets(mode, kw):
+    """BASELINE.json configs 2 and 4 (V=5, C=32, D=384, 688x464): the whole volume is built in one launch;
+    plane subsets are checked against the reference's ATen path on this GPU (the full ATen volume needs
+    47 GB of temporaries), and a slice launch must reproduce the same planes bit for bit."""
+    rig = synth.make_rig(num_views=5)
+    h, w, c, d = 688, 464, 32, 384
+    feats = synth.make_features(5, c, h, w, seed=0).to(DEV)
+    proj = torch.from_numpy(rig.proj(4)).unsqueeze(0).to(DEV)
+    hyps = synth.uniform_hypotheses(rig.dmin, rig.dmax, d, device=DEV)
+    tex = sweep.to_texels(feats)
+    pose = sweep.relative_poses(proj[0])
+    vol = sweep.cost_volume(tex, pose, hyps, mode, **kw)
+    assert torch.isfinite(vol[:, ::37]).all()
+    views = [feats[i:i + 1] for i in range(5)]
+    for d0 in (0, 190, 380):
+        sub = hyps[d0:d0 + 4].unsqueeze(0)
+        if mode == sweep.AGG_VARIANCE:
+            want = sweep_torch.variance_volume(views, proj, sub)[0]
+        else:
+            want = sweep_torch.groupwise_correlation_volume(views, proj, sub, kw["groups"])[0]
+        assert rel_norm_err(vol[:, d0:d0 + 4], want) < VOL_TOL
+        part = sweep.cost_volume(tex, pose, hyps, mode, d_begin=d0, d_count=4, **kw)
+        assert torch.equal(part, vol[:, d0:d0 + 4])
+    # source views are interchangeable for the aggregate (up to summation order)
+    perm = [0, 3, 1, 4, 2]
+    vol_p = sweep.cost_volume(tex[perm].contiguous(), sweep.relative_poses(proj[0][perm]), hyps, mode, d_begin=100,
+                              d_count=8, **kw)
+    assert rel_norm_err(vol_p, vol[:, 100:108]) < 1e-5
+    del vol
+    torch.cuda.empty_cache()
+
+
+def test_full_size_regression_against_cuda_aten():
+    d, h, w = 384, 688, 464
+    logits = synth.planted_logits(d, h, w, seed=1).to(DEV)
+    hyps = synth.uniform_hypotheses(400.0, 600.0, d, device=DEV)
+    depth, cf, idx = sweep_torch.regress_maxprob(logits.unsqueeze(0), hyps.unsqueeze(0))
+    r = sweep.depth_regress(logits, hyps)
+    assert _depth_err(r["depth"], depth[0]) < DEPTH_TOL
+    assert (r["index"].long() == idx[0]).float().mean() >= 0.999
+    # shift invariance of the softmax: adding a constant to every logit changes nothing
+    r2 = sweep.depth_regress(logits + 3.0, hyps)
+    assert _depth_err(r2["depth"], r["depth"]) < 1e-5
