@@ -35,6 +35,7 @@ int sweep_base_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaSt
 int sweep_base_group_corr(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream);
 int sweep_base_weighted_product(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream);
 int sweep_base_pair_mean(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream);
+int sweep_fast_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 
 static int sm_count() {
     static int cached = 0;
@@ -135,6 +136,12 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
     dim3 grid((unsigned)tiles, (unsigned)chunks);
     cudaStream_t stream = (cudaStream_t)cuda_stream;
 
+    // variant 0: production kernel, 2: production kernel with __fdiv_rn instead of the shared-reciprocal division,
+    // 1: baseline kernel.  Shapes the production kernel is not instantiated for use the baseline.
+    if (a->variant != 1 && a->mode == D3D_AGG_VARIANCE) {
+        int rc = sweep_fast_variance(cpt, nv, p, grid, stream, a->variant == 2);
+        if (rc >= 0) return rc;
+    }
     switch (a->mode) {
         case D3D_AGG_WARP: return sweep_base_warp(cpt, nv, p, grid, stream);
         case D3D_AGG_VARIANCE: return sweep_base_variance(cpt, nv, p, grid, stream);

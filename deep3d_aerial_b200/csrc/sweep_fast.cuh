@@ -1,0 +1,330 @@
+// Fused plane sweep, production kernel ("variant 0").
+//
+// Decomposition (C = 8*LPP channels, LPP in {1,2,4,8}):
+//   lane   = (pixel q of the warp, channel group cg of 8 channels);  LPP lanes share a pixel
+//   warp   = 32/LPP consecutive reference pixels x all channels
+//   group  = LPP warps = 32 consecutive pixels (one 128-byte row segment per output channel)
+//   CTA    = 8 warps = 8/LPP groups;  blockIdx.y = chunk of depth planes
+// Every thread walks its depth planes in order and keeps, per source view, the 2x2 texel footprint of
+// its 8 channels in registers (128 registers at 4 source views); a footprint is re-fetched only when
+// floor(ix), floor(iy) move, so the bilinear gather runs out of registers for ~1/travel planes.
+//
+// What makes it fast (numbers from tools/microbench.cu and the ncu captures under profiles/):
+//  * the projection is computed ONCE per (pixel, view, plane): the LPP lanes of a pixel split the source
+//    views and publish {fx, fy, fx*fy, key} through a per-warp double-buffered shared-memory table, one
+//    plane ahead; consumers fetch it with one broadcast LDS.128 per view;
+//  * bilinear interpolation as  A + fx*B + fy*C + fx*fy*D  (B=b-a, C=c-a, D=a-b-c+d, rebuilt whenever a
+//    footprint arrives): 3 FMAs per channel instead of 4;
+//  * packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2, new on sm_100) over channel pairs.  FFMA2 has the
+//    FP32 pipe throughput of two FFMAs but takes ONE issue slot; the kernel is issue-bound, so this is
+//    what makes room for the address, shared-memory and store instructions;
+//  * the whole plane is ONE basic block: the four views' footprint keys are compared with a single
+//    branch, the (rare) re-fetch is an opaque PTX block that updates the cache in place;
+//  * stores: 32-byte row segments reach only 2.3 TB/s on B200, 128-byte ones 7.3 TB/s -> results go
+//    through an XOR-swizzled [planes][C][32 px] shared-memory tile per group (conflict-free STS.32 in,
+//    LDS.128 out) and leave as full 128-byte rows with STG.128; the LPP warps of a group meet at a named
+//    barrier once per kTilePlanes planes (double-buffered tile).
+#pragma once
+#include "common.cuh"
+#include "sweep_refetch.cuh"
+
+namespace d3d {
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 splat(float a) { return make_float2(a, a); }
+
+// key = [31:28] in-bounds mask of the corners nw, ne, sw, se | [27:14] y0+4 | [13:0] x0+4
+constexpr float kMagic = 12582912.f;           // 1.5 * 2^23: float(kMagic + n) has bits 0x4B400000 + n
+constexpr int kMagicBits = 0x4B400000;
+constexpr int kTilePlanes = 4;                 // planes staged per group barrier
+
+// Two quotients by the same divisor, correctly rounded in all but pathological cases: one MUFU.RCP,
+// one Newton step on the reciprocal, and the residual correction  q' = q + (x - q*z) * r  that IEEE
+// division itself ends with -- without its special-case path (z is a depth-like positive number
+// here; garbage in gives garbage that the caller clamps out of bounds).
+__device__ __forceinline__ void div2(float x, float y, float z, float& u, float& v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(z));
+    r = fmaf(fmaf(-z, r, 1.f), r, r);
+    float qu = x * r, qv = y * r;
+    u = fmaf(fmaf(-qu, z, x), r, qu);
+    v = fmaf(fmaf(-qv, z, y), r, qv);
+}
+
+// Projection of one reference pixel onto one source view at one depth, with the fp32 operation order
+// of the reference + CUDA-ATen (tools/diag_coords.py checked each step bit for bit on B200):
+//   module.py:538      ray = rot @ [x,y,1]        fma(r2,1,fma(r1,y,r0*x))         (cuBLAS)
+//   module.py:539-541  X = ray*d (rounded) + t (rounded)
+//   module.py:542      u = X/Z  correctly rounded division
+//   module.py:543      g = u * f32(1/((W-1)/2)) - 1          (ATen-CUDA multiplies by the reciprocal)
+//   GridSampler.h:31   ix = ((g + 1) * 0.5) * (W-1)
+template <bool kIeeeDiv>
+__device__ __forceinline__ float4 project_frac(float rx, float ry, float rz, float tx, float ty, float tz, float d,
+                                               const SweepParams& p) {
+    float X = __fadd_rn(__fmul_rn(rx, d), tx);
+    float Y = __fadd_rn(__fmul_rn(ry, d), ty);
+    float Z = __fadd_rn(__fmul_rn(rz, d), tz);
+    float u, v;
+    if (kIeeeDiv) {
+        u = __fdiv_rn(X, Z);
+        v = __fdiv_rn(Y, Z);
+    } else {
+        div2(X, Y, Z, u, v);
+    }
+    float ix = __fmul_rn(__fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(u, p.inv_half_w), 1.f), 1.f), 0.5f), p.wm1);
+    float iy = __fmul_rn(__fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(v, p.inv_half_h), 1.f), 1.f), 0.5f), p.hm1);
+    ix = fminf(fmaxf(ix, -2.f), p.wm1 + 2.f);   // NaN -> -2: every corner out of bounds
+    iy = fminf(fmaxf(iy, -2.f), p.hm1 + 2.f);
+    // floor without the XU pipe: round to nearest through the magic constant, step down if above
+    float mx = __fadd_rn(ix, kMagic), my = __fadd_rn(iy, kMagic);
+    float fx0 = __fsub_rn(mx, kMagic), fy0 = __fsub_rn(my, kMagic);
+    int xi = __float_as_int(mx) - kMagicBits, yi = __float_as_int(my) - kMagicBits;
+    if (fx0 > ix) { fx0 -= 1.f; xi -= 1; }
+    if (fy0 > iy) { fy0 -= 1.f; yi -= 1; }
+    const float fx = __fsub_rn(ix, fx0), fy = __fsub_rn(iy, fy0);
+    const bool x0in = (unsigned)xi < (unsigned)p.W, x1in = (unsigned)(xi + 1) < (unsigned)p.W;
+    const bool y0in = (unsigned)yi < (unsigned)p.H, y1in = (unsigned)(yi + 1) < (unsigned)p.H;
+    unsigned key = ((unsigned)(yi + 4) << 14) | (unsigned)(xi + 4);
+    key |= (x0in && y0in) ? (1u << 28) : 0u;
+    key |= (x1in && y0in) ? (1u << 29) : 0u;
+    key |= (x0in && y1in) ? (1u << 30) : 0u;
+    key |= (x1in && y1in) ? (1u << 31) : 0u;
+    return make_float4(fx, fy, fx * fy, __uint_as_float(key));
+}
+
+__device__ __forceinline__ void group_barrier(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int NV, int LPP, int MODE, bool kIeeeDiv>
+__global__ void __launch_bounds__(256, 1) sweep_fast_kernel(const SweepParams p) {
+    constexpr int CPT = 8;
+    constexpr int PPW = 32 / LPP;                 // pixels per warp
+    constexpr int KV = (NV + LPP - 1) / LPP;      // views whose projection this lane owns
+    constexpr int NP = CPT / 2;                   // channel pairs per lane
+    constexpr int C = CPT * LPP;
+    constexpr int GROUPS = 8 / LPP;               // 32-pixel groups per CTA
+    constexpr int TILE = kTilePlanes * C * 32;    // floats per tile buffer
+    extern __shared__ float4 smem4[];
+    float4(*geo)[2][NV][PPW] = reinterpret_cast<float4(*)[2][NV][PPW]>(smem4);          // [8 warps]
+    float* tile = reinterpret_cast<float*>(smem4 + 8 * 2 * NV * PPW);                   // [GROUPS][2][TILE]
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int cg = lane % LPP;
+    const int q = lane / LPP;
+    const int grp = warp / LPP, wq = warp % LPP;  // group of the CTA, warp within the group
+    const int choff = cg * CPT;
+    const long long grp_base = ((long long)blockIdx.x * GROUPS + grp) * 32;
+    const long long pix_raw = grp_base + wq * PPW + q;
+    const int pix = pix_raw < p.HW ? (int)pix_raw : p.HW - 1;   // clamp: the warp stays whole
+    const int py = pix / p.W, px = pix - py * p.W;
+
+    const int d0 = p.d_begin + blockIdx.y * p.d_chunk;
+    const int d1 = min(d0 + p.d_chunk, p.d_end);
+    if (d0 >= d1) return;
+
+    float rx[KV], ry[KV], rz[KV], tx[KV], ty[KV], tz[KV];
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+        const int v = min(cg + k * LPP, NV - 1);
+        const float* m = p.pose + v * 16;
+        rx[k] = fmaf(m[2], 1.f, fmaf(m[1], (float)py, m[0] * (float)px));
+        ry[k] = fmaf(m[6], 1.f, fmaf(m[5], (float)py, m[4] * (float)px));
+        rz[k] = fmaf(m[10], 1.f, fmaf(m[9], (float)py, m[8] * (float)px));
+        tx[k] = m[3]; ty[k] = m[7]; tz[k] = m[11];
+    }
+
+    float2 rf[NP], rf2[NP];
+    {
+        const float* t = p.feats + (size_t)pix * C + choff;
+#pragma unroll
+        for (int k = 0; k < CPT; k += 4) {
+            float4 w = ldg4(t + k);
+            rf[k / 2] = f2(w.x, w.y);
+            rf[k / 2 + 1] = f2(w.z, w.w);
+        }
+#pragma unroll
+        for (int j = 0; j < NP; ++j) rf2[j] = __fmul2_rn(rf[j], rf[j]);
+    }
+
+    float2 tex[NV][4][NP];      // per view: A, B, C, D of the current 2x2 footprint
+    unsigned ckey[NV];
+    const float* vbase[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        ckey[v] = 0xffffffffu;
+        vbase[v] = p.feats + (size_t)(v + 1) * p.HW * C + choff;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < NP; ++j) tex[v][k][j] = f2(0.f, 0.f);
+    }
+    const int row_bytes = p.W * C * 4;
+
+    const size_t hyp_stride = p.perpix ? (size_t)p.HW : 1;
+    const float* hp = p.hyps + (p.perpix ? (size_t)pix : 0);
+
+    auto publish = [&](int buf, float depth) {
+#pragma unroll
+        for (int k = 0; k < KV; ++k) {
+            const int v = cg + k * LPP;
+            if (NV % LPP == 0 || v < NV)
+                geo[warp][buf][v][q] = project_frac<kIeeeDiv>(rx[k], ry[k], rz[k], tx[k], ty[k], tz[k], depth, p);
+        }
+    };
+
+    // prologue: geometry of the first plane
+    float dnext = __ldg(hp + (size_t)d0 * hyp_stride);
+    publish(d0 & 1, dnext);
+    if (d0 + 1 < d1) dnext = __ldg(hp + (size_t)(d0 + 1) * hyp_stride);
+
+    const float invV = 1.f / (float)(NV + 1);
+    // staging tile: element (plane t, channel row r, pixel column c) lives at  t*C*32 + r*32 + (c ^ swz(r)),
+    // swz(r) = PPW*(r>>3) & 31, which spreads the LPP channel groups of one pixel over distinct banks and
+    // keeps every aligned run of 4 pixels contiguous for the 16-byte read-out
+    float* tbase = tile + (size_t)grp * 2 * TILE;
+    const int col = wq * PPW + q;
+    // this lane's 8 channel rows share r>>3 == cg, so its STS offsets are s0 + 32*k
+    const int s0 = choff * 32 + (col ^ ((PPW * cg) & 31));
+    // read-out: 2 float4 per lane per plane; item i -> row, 4-pixel column chunk
+    const int t_in_grp = wq * 32 + lane;
+    int rrow[2], rc4[2], roff[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = t_in_grp + i * LPP * 32;
+        rrow[i] = idx >> 3;
+        rc4[i] = (idx & 7) * 4;
+        roff[i] = rrow[i] * 32 + (rc4[i] ^ ((PPW * (rrow[i] >> 3)) & 31));
+    }
+    const bool vec_ok = ((p.out_sc | p.out_sd) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+
+    const bool fast_rows = vec_ok && grp_base + 32 <= p.HW;      // whole group in range, 16-byte stores
+    auto flush = [&](int buf, int first_plane, int nplanes) {     // tile buffer -> global, 128-byte rows
+        const float* t = tbase + (size_t)buf * TILE;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const long long gp = grp_base + rc4[i];
+            float* orow = p.out + (size_t)rrow[i] * p.out_sc + (size_t)(first_plane - p.d_begin) * p.out_sd + gp;
+            const float* ti = t + roff[i];
+            if (fast_rows && nplanes == kTilePlanes) {
+                float4 w[kTilePlanes];
+#pragma unroll
+                for (int tp = 0; tp < kTilePlanes; ++tp) w[tp] = *reinterpret_cast<const float4*>(ti + tp * C * 32);
+#pragma unroll
+                for (int tp = 0; tp < kTilePlanes; ++tp) *reinterpret_cast<float4*>(orow + (size_t)tp * p.out_sd) = w[tp];
+            } else {
+                for (int tp = 0; tp < nplanes; ++tp) {
+                    const float4 w = *reinterpret_cast<const float4*>(ti + tp * C * 32);
+                    float* o = orow + (size_t)tp * p.out_sd;
+                    if (gp < p.HW) o[0] = w.x;
+                    if (gp + 1 < p.HW) o[1] = w.y;
+                    if (gp + 2 < p.HW) o[2] = w.z;
+                    if (gp + 3 < p.HW) o[3] = w.w;
+                }
+            }
+        }
+    };
+
+    int staged = 0, batch = 0;                       // planes in the current tile buffer, buffer parity
+    for (int dd = d0; dd < d1; ++dd) {
+        __syncwarp();                                // geo[dd&1] is complete; geo[(dd+1)&1] is free
+        if (dd + 1 < d1) {
+            publish((dd + 1) & 1, dnext);
+            if (dd + 2 < d1) dnext = __ldg(hp + (size_t)(dd + 2) * hyp_stride);
+        }
+        float4 g[NV];
+        unsigned moved = 0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            g[v] = geo[warp][dd & 1][v][q];
+            moved |= __float_as_uint(g[v].w) ^ ckey[v];
+        }
+        if (moved) {                                 // some footprint moved: re-fetch those (in place)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const unsigned key = __float_as_uint(g[v].w);
+                refetch_footprint(tex[v], key, ckey[v], vbase[v], p.W - 1, p.H - 1, row_bytes, C * 4);
+                ckey[v] = key;
+            }
+        }
+
+        float2 s[NP], sq[NP];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const float2 fx = splat(g[v].x), fy = splat(g[v].y), fxy = splat(g[v].z);
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                float2 o = __ffma2_rn(fx, tex[v][1][j], tex[v][0][j]);
+                o = __ffma2_rn(fy, tex[v][2][j], o);
+                o = __ffma2_rn(fxy, tex[v][3][j], o);
+                if (MODE == D3D_AGG_VARIANCE) {
+                    if (v == 0) {
+                        s[j] = __fadd2_rn(rf[j], o);
+                        sq[j] = __ffma2_rn(o, o, rf2[j]);
+                    } else {
+                        s[j] = __fadd2_rn(s[j], o);
+                        sq[j] = __ffma2_rn(o, o, sq[j]);
+                    }
+                }
+            }
+        }
+
+        float2 r[NP];
+        if (MODE == D3D_AGG_VARIANCE) {
+            const float2 ninv = splat(-invV), pinv = splat(invV);
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                float2 t = __fmul2_rn(s[j], ninv);                  // -sum/V
+                float2 w = __ffma2_rn(t, s[j], sq[j]);               // sq - sum^2/V
+                r[j] = __fmul2_rn(w, pinv);                          // sq/V - (sum/V)^2
+            }
+        }
+        if (LPP == 1) {                              // the warp already owns 32 consecutive pixels
+            float* oplane = p.out + (size_t)(dd - p.d_begin) * p.out_sd;
+            if (pix_raw < p.HW) {
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    oplane[(size_t)(2 * j) * p.out_sc + pix] = r[j].x;
+                    oplane[(size_t)(2 * j + 1) * p.out_sc + pix] = r[j].y;
+                }
+            }
+        } else {
+            float* t = tbase + (size_t)batch * TILE + staged * C * 32;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                t[s0 + 64 * j] = r[j].x;
+                t[s0 + 64 * j + 32] = r[j].y;
+            }
+            if (++staged == kTilePlanes || dd + 1 == d1) {
+                group_barrier(1 + grp, LPP * 32);
+                flush(batch, dd + 1 - staged, staged);
+                staged = 0;
+                batch ^= 1;
+            }
+        }
+    }
+}
+
+template <int NV, int LPP>
+constexpr size_t sweep_fast_smem() {
+    return (size_t)8 * 2 * NV * (32 / LPP) * sizeof(float4) +
+           (LPP > 1 ? (size_t)(8 / LPP) * 2 * kTilePlanes * 8 * LPP * 32 * sizeof(float) : 0);
+}
+
+template <int NV, int LPP, int MODE>
+int launch_sweep_fast(const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div) {
+    constexpr size_t smem = sweep_fast_smem<NV, LPP>();
+    auto kern = ieee_div ? sweep_fast_kernel<NV, LPP, MODE, true> : sweep_fast_kernel<NV, LPP, MODE, false>;
+    static bool configured[2] = {false, false};      // per instantiation, per division flavour
+    if (!configured[ieee_div]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(D3D_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+        configured[ieee_div] = true;
+    }
+    kern<<<grid, 256, smem, stream>>>(p);
+    count_launch();
+    return check_launch("sweep_fast_kernel");
+}
+
+}  // namespace d3d

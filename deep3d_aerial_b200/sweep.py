@@ -56,10 +56,14 @@ def to_texels(features, out: Optional[torch.Tensor] = None) -> torch.Tensor:
 
 
 def relative_poses(proj: torch.Tensor) -> torch.Tensor:
-    """[V,4,4] projection matrices (view 0 = reference) -> [V-1,4,4] P_src @ inverse(P_ref), computed
-    with the very ops of the reference (mvs/mvs_cas/models/module.py:528) so the matrices the kernel
-    sees are the matrices the reference sees."""
-    return torch.matmul(proj[1:], torch.inverse(proj[:1])).contiguous()
+    """[V,4,4] projection matrices (view 0 = reference) -> [V-1,4,4] P_src @ inverse(P_ref).
+
+    Computed with the very calls of the reference (mvs/mvs_cas/models/module.py:528, one [1,4,4] matmul
+    per source view) so the kernel sees bit for bit the matrices the reference sees: a batched matmul
+    rounds 1.6 % of the entries differently on B200 (tools/diag_coords.py), which is enough to move
+    projected coordinates by an ulp and the cost volume by 1e-4 at production image sizes."""
+    inv = torch.inverse(proj[0:1])
+    return torch.cat([torch.matmul(proj[i:i + 1], inv) for i in range(1, proj.shape[0])], 0).contiguous()
 
 
 def cost_volume(texels: torch.Tensor, pose: torch.Tensor, hyps: torch.Tensor, mode: int = AGG_VARIANCE, *,

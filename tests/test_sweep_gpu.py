@@ -188,26 +188,43 @@ CASES = [  # v, c, d, h, w, perpixel
 ]
 
 
+# kernel variants (include/d3d_sweep.h): 0 = production kernel, 1 = baseline kernel, 2 = production kernel
+# with reciprocal-multiply instead of the correctly rounded division
+VARIANTS = [0, 1, 2]
+
+
 @pytest.mark.parametrize("v,c,d,h,w,perpixel", CASES)
 @pytest.mark.parametrize("oracle_dev", ["cpu", "cuda"])
-def test_variance_matches_oracle(v, c, d, h, w, perpixel, oracle_dev):
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_variance_matches_oracle(v, c, d, h, w, perpixel, oracle_dev, variant):
     _, proj, feats, hyps = _scene(v, c, d, h, w, seed=3, perpixel=perpixel)
     want = sweep_torch.variance_volume([f.to(oracle_dev) for f in _views(feats)], proj.to(oracle_dev),
                                        hyps.to(oracle_dev))[0]
-    got = _ours_volume(feats, proj, hyps, sweep.AGG_VARIANCE)
+    got = _ours_volume(feats, proj, hyps, sweep.AGG_VARIANCE, variant=variant)
     assert got.shape == want.shape
     assert rel_norm_err(got, want) < VOL_TOL
 
 
+@pytest.mark.parametrize("d", [1, 2, 3, 7])
+def test_short_sweeps_and_depth_chunks(d):
+    """Few planes on a small image: the launch splits the sweep into depth chunks (blockIdx.y) to fill the
+    SMs; every chunk re-warms its footprints and must agree with the oracle."""
+    _, proj, feats, hyps = _scene(5, 32, d, 24, 20, seed=12)
+    want = sweep_torch.variance_volume(_views(feats), proj, hyps)[0]
+    for variant in VARIANTS:
+        assert rel_norm_err(_ours_volume(feats, proj, hyps, sweep.AGG_VARIANCE, variant=variant), want) < VOL_TOL
+
+
 @pytest.mark.parametrize("smooth", [False, True])
-def test_whu_shaped_rig_matches_oracle(smooth):
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_whu_shaped_rig_matches_oracle(smooth, variant):
     """The WHU-OMVS cross rig of SURVEY.md §8d (f=4000 at 1856x2752, 40 m baselines, 400-600 m) on a crop-sized
     feature map: coordinates of the production magnitude, so fp32 rounding of the projection matters."""
     rig = synth.make_rig(num_views=5)
     h, w, d, c = 172, 116, 12, 32          # 1/16 of full res: scale 16 keeps the full-size geometry
     _, proj, feats, hyps = _scene(5, c, d, h, w, seed=5, smooth=smooth, rig=rig, scale=16)
     want = sweep_torch.variance_volume(_cuda_views(feats), proj.to(DEV), hyps.to(DEV))[0]
-    got = _ours_volume(feats, proj, hyps, sweep.AGG_VARIANCE)
+    got = _ours_volume(feats, proj, hyps, sweep.AGG_VARIANCE, variant=variant)
     assert rel_norm_err(got, want) < VOL_TOL
 
 
@@ -336,7 +353,8 @@ def test_texel_relayout_round_trip():
 
 
 # ------------------------------------------------------------------ (3) properties at full size
-@pytest.mark.parametrize("mode,kw", [(sweep.AGG_VARIANCE, {}), (sweep.AGG_GROUP_CORR, {"groups": 8})])
+@pytest.mark.parametrize("mode,kw", [(sweep.AGG_VARIANCE, {"variant": 0}), (sweep.AGG_VARIANCE, {"variant": 1}),
+                                     (sweep.AGG_VARIANCE, {"variant": 2}), (sweep.AGG_GROUP_CORR, {"groups": 8})])
 def test_full_size_config_against_cuda_aten_on_plane_subsets(mode, kw):
     """BASELINE.json configs 2 and 4 (V=5, C=32, D=384, 688x464): the whole volume is built in one launch;
     plane subsets are checked against the reference's ATen path on this GPU (the full ATen volume needs
@@ -357,7 +375,9 @@ def test_full_size_config_against_cuda_aten_on_plane_subsets(mode, kw):
             want = sweep_torch.variance_volume(views, proj, sub)[0]
         else:
             want = sweep_torch.groupwise_correlation_volume(views, proj, sub, kw["groups"])[0]
-        assert rel_norm_err(vol[:, d0:d0 + 4], want) < VOL_TOL
+        err = rel_norm_err(vol[:, d0:d0 + 4], want)
+        print("full-size planes %d..%d %s: rel err %.3e" % (d0, d0 + 3, kw, err))
+        assert err < VOL_TOL
         part = sweep.cost_volume(tex, pose, hyps, mode, d_begin=d0, d_count=4, **kw)
         assert torch.equal(part, vol[:, d0:d0 + 4])
     # source views are interchangeable for the aggregate (up to summation order)
