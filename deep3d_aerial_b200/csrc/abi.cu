@@ -116,32 +116,47 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
     p.out_sd = a->out_stride_d > 0 ? a->out_stride_d : p.HW;
     p.out_sc = a->out_stride_c > 0 ? a->out_stride_c : (long long)d_count * p.out_sd;
     p.d_begin = d_begin; p.d_end = d_begin + d_count;
-    p.lpp_log2 = lpp_log2; p.perpix = a->hyps_per_pixel != 0;
+    p.perpix = a->hyps_per_pixel != 0;
     p.groups = a->groups; p.eps_num = a->eps_in_numerator != 0;
+    p.flags = 0;
     p.inv_half_w = 1.f / ((float)(a->width - 1) / 2.f);
     p.inv_half_h = 1.f / ((float)(a->height - 1) / 2.f);
     p.wm1 = (float)(a->width - 1); p.hm1 = (float)(a->height - 1);
 
     // grid: x = pixel tiles (8 warps x 32/LPP pixels), y = depth chunks.  Depth is only split when
     // the pixel tiles alone leave SMs idle (each chunk re-warms its footprint registers).
-    const int pix_per_cta = 8 * (32 >> lpp_log2);
-    const long long tiles = ((long long)p.HW + pix_per_cta - 1) / pix_per_cta;
-    int chunks = 1;
-    const long long want = 4LL * sm_count();
-    if (tiles < want) chunks = (int)((want + tiles - 1) / tiles);
-    if (chunks > d_count) chunks = d_count;
-    p.d_chunk = (d_count + chunks - 1) / chunks;
-    chunks = (d_count + p.d_chunk - 1) / p.d_chunk;
-    if (tiles > 0x7fffffffLL || chunks > 65535) return fail(D3D_ERR_UNSUPPORTED, "d3d_cost_volume: grid too large");
-    dim3 grid((unsigned)tiles, (unsigned)chunks);
     cudaStream_t stream = (cudaStream_t)cuda_stream;
+    auto make_grid = [&](int lpp_l2, dim3& grid) -> int {
+        p.lpp_log2 = lpp_l2;
+        const int pix_per_cta = 8 * (32 >> lpp_l2);
+        const long long tiles = ((long long)p.HW + pix_per_cta - 1) / pix_per_cta;
+        int chunks = 1;
+        const long long want = 4LL * sm_count();
+        if (tiles < want) chunks = (int)((want + tiles - 1) / tiles);
+        if (chunks > d_count) chunks = d_count;
+        p.d_chunk = (d_count + chunks - 1) / chunks;
+        chunks = (d_count + p.d_chunk - 1) / p.d_chunk;
+        if (tiles > 0x7fffffffLL || chunks > 65535) return fail(D3D_ERR_UNSUPPORTED, "d3d_cost_volume: grid too large");
+        grid = dim3((unsigned)tiles, (unsigned)chunks);
+        return D3D_OK;
+    };
+    dim3 grid;
 
-    // variant 0: production kernel, 2: production kernel with __fdiv_rn instead of the shared-reciprocal division,
+    // variant 0: production kernel (4 channels per lane where C <= 32, else 8); 3: production kernel with
+    // 8 channels per lane; 2: variant 0 with __fdiv_rn instead of the shared-reciprocal division;
     // 1: baseline kernel.  Shapes the production kernel is not instantiated for use the baseline.
-    if (a->variant != 1 && a->mode == D3D_AGG_VARIANCE) {
-        int rc = sweep_fast_variance(cpt, nv, p, grid, stream, a->variant == 2);
-        if (rc >= 0) return rc;
+    const int variant = a->variant & 15;
+    if (variant != 1 && a->mode == D3D_AGG_VARIANCE && nv <= 4) {
+        int fcpt = (variant == 3 && C % 8 == 0) ? 8 : 4;
+        int fl2 = ilog2_exact(C / fcpt);
+        if ((fl2 < 0 || fl2 > 3) && C % 8 == 0) { fcpt = 8; fl2 = ilog2_exact(C / 8); }
+        if (fl2 >= 0 && fl2 <= 3) {
+            if (int rc = make_grid(fl2, grid)) return rc;
+            int rc = sweep_fast_variance(fcpt, nv, p, grid, stream, variant == 2);
+            if (rc >= 0) return rc;
+        }
     }
+    if (int rc = make_grid(lpp_log2, grid)) return rc;
     switch (a->mode) {
         case D3D_AGG_WARP: return sweep_base_warp(cpt, nv, p, grid, stream);
         case D3D_AGG_VARIANCE: return sweep_base_variance(cpt, nv, p, grid, stream);

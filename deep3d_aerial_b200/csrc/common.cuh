@@ -28,6 +28,7 @@ struct SweepParams {
     int lpp_log2;         // log2(lanes per pixel) = log2(C / CPT)
     int perpix;           // hyps layout
     int groups, eps_num;
+    int flags;            // bit 0: prefetch moved footprints one pass ahead
     float inv_half_w, inv_half_h;  // 1/((W-1)/2), 1/((H-1)/2)   (module.py:543-544)
     float wm1, hm1;                // W-1, H-1                   (GridSampler.h:27-32)
 };

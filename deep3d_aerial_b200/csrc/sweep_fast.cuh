@@ -1,18 +1,21 @@
 // Fused plane sweep, production kernel ("variant 0").
 //
-// Decomposition (C = 8*LPP channels, LPP in {1,2,4,8}):
-//   lane   = (pixel q of the warp, channel group cg of 8 channels);  LPP lanes share a pixel
+// Decomposition (C = CPT*LPP channels; CPT = 4 or 8 channels per lane, LPP in {1,2,4,8} lanes per pixel):
+//   lane   = (pixel q of the warp, channel group cg of CPT channels);  LPP lanes share a pixel
 //   warp   = 32/LPP consecutive reference pixels x all channels
 //   group  = LPP warps = 32 consecutive pixels (one 128-byte row segment per output channel)
 //   CTA    = 8 warps = 8/LPP groups;  blockIdx.y = chunk of depth planes
 // Every thread walks its depth planes in order and keeps, per source view, the 2x2 texel footprint of
-// its 8 channels in registers (128 registers at 4 source views); a footprint is re-fetched only when
-// floor(ix), floor(iy) move, so the bilinear gather runs out of registers for ~1/travel planes.
+// its CPT channels in registers (64 / 128 registers at 4 source views); a footprint is re-fetched only
+// when floor(ix), floor(iy) move, so the bilinear gather runs out of registers for ~1/travel planes.
+// CPT = 4 fits 128 registers per thread -> 16 resident warps per SM instead of 8 (the kernel is
+// latency-bound at 8, profiles/).
 //
 // What makes it fast (numbers from tools/microbench.cu and the ncu captures under profiles/):
 //  * the projection is computed ONCE per (pixel, view, plane): the LPP lanes of a pixel split the source
-//    views and publish {fx, fy, fx*fy, key} through a per-warp double-buffered shared-memory table, one
-//    plane ahead; consumers fetch it with one broadcast LDS.128 per view;
+//    views (and, when there are more lanes than views, two consecutive planes) and publish
+//    {fx, fy, fx*fy, key} through a per-warp double-buffered shared-memory table, one pass ahead;
+//    consumers fetch it with one broadcast LDS.128 per view;
 //  * bilinear interpolation as  A + fx*B + fy*C + fx*fy*D  (B=b-a, C=c-a, D=a-b-c+d, rebuilt whenever a
 //    footprint arrives): 3 FMAs per channel instead of 4;
 //  * packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2, new on sm_100) over channel pairs.  FFMA2 has the
@@ -36,7 +39,7 @@ __device__ __forceinline__ float2 splat(float a) { return make_float2(a, a); }
 // key = [31:28] in-bounds mask of the corners nw, ne, sw, se | [27:14] y0+4 | [13:0] x0+4
 constexpr float kMagic = 12582912.f;           // 1.5 * 2^23: float(kMagic + n) has bits 0x4B400000 + n
 constexpr int kMagicBits = 0x4B400000;
-constexpr int kTilePlanes = 4;                 // planes staged per group barrier
+constexpr int kTilePlanes = 8;                 // planes staged per group barrier
 
 // Two quotients by the same divisor, correctly rounded in all but pathological cases: one MUFU.RCP,
 // one Newton step on the reciprocal, and the residual correction  q' = q + (x - q*z) * r  that IEEE
@@ -96,38 +99,43 @@ __device__ __forceinline__ void group_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int NV, int LPP, int MODE, bool kIeeeDiv>
-__global__ void __launch_bounds__(256, 1) sweep_fast_kernel(const SweepParams p) {
-    constexpr int CPT = 8;
-    constexpr int PPW = 32 / LPP;                 // pixels per warp
-    constexpr int KV = (NV + LPP - 1) / LPP;      // views whose projection this lane owns
-    constexpr int NP = CPT / 2;                   // channel pairs per lane
+template <int CPT, int NV, int LPP, int MODE, bool kIeeeDiv>
+__global__ void __launch_bounds__(256, (CPT == 4 ? 2 : 1)) sweep_fast_kernel(const SweepParams p) {
+    constexpr int PPW = 32 / LPP;                          // pixels per warp
+    constexpr int PB = (LPP >= 2 * NV) ? 2 : 1;            // planes published per geometry pass
+    constexpr int KV = (LPP >= NV) ? 1 : (NV + LPP - 1) / LPP;   // projections a lane owns per pass
+    constexpr int NP = CPT / 2;                            // channel pairs per lane
     constexpr int C = CPT * LPP;
-    constexpr int GROUPS = 8 / LPP;               // 32-pixel groups per CTA
-    constexpr int TILE = kTilePlanes * C * 32;    // floats per tile buffer
+    constexpr int GROUPS = 8 / LPP;                        // 32-pixel groups per CTA
+    constexpr int TILE = kTilePlanes * C * 32;             // floats per tile buffer
+    constexpr int NRO = CPT / 4;                           // float4 each lane moves per plane at read-out
     extern __shared__ float4 smem4[];
-    float4(*geo)[2][NV][PPW] = reinterpret_cast<float4(*)[2][NV][PPW]>(smem4);          // [8 warps]
-    float* tile = reinterpret_cast<float*>(smem4 + 8 * 2 * NV * PPW);                   // [GROUPS][2][TILE]
+    float4(*geo)[2][PB][NV][PPW] = reinterpret_cast<float4(*)[2][PB][NV][PPW]>(smem4);   // [8 warps]
+    float* tile = reinterpret_cast<float*>(smem4 + 8 * 2 * PB * NV * PPW);               // [GROUPS][2][TILE]
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int cg = lane % LPP;
     const int q = lane / LPP;
-    const int grp = warp / LPP, wq = warp % LPP;  // group of the CTA, warp within the group
+    const int grp = warp / LPP, wq = warp % LPP;           // group of the CTA, warp within the group
     const int choff = cg * CPT;
     const long long grp_base = ((long long)blockIdx.x * GROUPS + grp) * 32;
     const long long pix_raw = grp_base + wq * PPW + q;
-    const int pix = pix_raw < p.HW ? (int)pix_raw : p.HW - 1;   // clamp: the warp stays whole
+    const int pix = pix_raw < p.HW ? (int)pix_raw : p.HW - 1;    // clamp: the warp stays whole
     const int py = pix / p.W, px = pix - py * p.W;
 
     const int d0 = p.d_begin + blockIdx.y * p.d_chunk;
     const int d1 = min(d0 + p.d_chunk, p.d_end);
     if (d0 >= d1) return;
 
+    // projection ownership: with LPP >= NV a lane owns (view cg % NV, plane offset cg / NV) of each pass;
+    // otherwise it owns views cg, cg + LPP, ... of the pass's single plane
+    const int po = (LPP >= NV) ? cg / NV : 0;
+    const bool owner = (LPP >= NV) ? (cg < PB * NV) : true;
     float rx[KV], ry[KV], rz[KV], tx[KV], ty[KV], tz[KV];
 #pragma unroll
     for (int k = 0; k < KV; ++k) {
-        const int v = min(cg + k * LPP, NV - 1);
+        const int v = (LPP >= NV) ? cg % NV : min(cg + k * LPP, NV - 1);
         const float* m = p.pose + v * 16;
         rx[k] = fmaf(m[2], 1.f, fmaf(m[1], (float)py, m[0] * (float)px));
         ry[k] = fmaf(m[6], 1.f, fmaf(m[5], (float)py, m[4] * (float)px));
@@ -165,79 +173,85 @@ __global__ void __launch_bounds__(256, 1) sweep_fast_kernel(const SweepParams p)
     const size_t hyp_stride = p.perpix ? (size_t)p.HW : 1;
     const float* hp = p.hyps + (p.perpix ? (size_t)pix : 0);
 
-    auto publish = [&](int buf, float depth) {
+    // projections of this lane's share of planes [base, base + PB): pure arithmetic, no branches, so the
+    // compiler can interleave this long dependent chain with the packed interpolation arithmetic
+    auto project_mine = [&](float4 (&gn)[KV], float depth) {
 #pragma unroll
-        for (int k = 0; k < KV; ++k) {
-            const int v = cg + k * LPP;
-            if (NV % LPP == 0 || v < NV)
-                geo[warp][buf][v][q] = project_frac<kIeeeDiv>(rx[k], ry[k], rz[k], tx[k], ty[k], tz[k], depth, p);
+        for (int k = 0; k < KV; ++k)
+            gn[k] = project_frac<kIeeeDiv>(rx[k], ry[k], rz[k], tx[k], ty[k], tz[k], depth, p);
+    };
+    auto store_mine = [&](const float4 (&gn)[KV], int buf, int base) {
+        if (owner && base + po < d1) {
+#pragma unroll
+            for (int k = 0; k < KV; ++k) {
+                const int v = (LPP >= NV) ? cg % NV : cg + k * LPP;
+                if (LPP >= NV || NV % LPP == 0 || v < NV) geo[warp][buf][po][v][q] = gn[k];
+            }
         }
     };
+    auto depth_of = [&](int plane) { return __ldg(hp + (size_t)min(plane, d1 - 1) * hyp_stride); };
 
-    // prologue: geometry of the first plane
-    float dnext = __ldg(hp + (size_t)d0 * hyp_stride);
-    publish(d0 & 1, dnext);
-    if (d0 + 1 < d1) dnext = __ldg(hp + (size_t)(d0 + 1) * hyp_stride);
+    // prologue: geometry of the first pass
+    float dnext = depth_of(d0 + po);
+    {
+        float4 gn[KV];
+        project_mine(gn, dnext);
+        store_mine(gn, 0, d0);
+    }
+    dnext = depth_of(d0 + PB + po);
 
     const float invV = 1.f / (float)(NV + 1);
     // staging tile: element (plane t, channel row r, pixel column c) lives at  t*C*32 + r*32 + (c ^ swz(r)),
-    // swz(r) = PPW*(r>>3) & 31, which spreads the LPP channel groups of one pixel over distinct banks and
+    // swz(r) = PPW*(r/CPT) & 31, which spreads the LPP channel groups of one pixel over distinct banks and
     // keeps every aligned run of 4 pixels contiguous for the 16-byte read-out
     float* tbase = tile + (size_t)grp * 2 * TILE;
     const int col = wq * PPW + q;
-    // this lane's 8 channel rows share r>>3 == cg, so its STS offsets are s0 + 32*k
-    const int s0 = choff * 32 + (col ^ ((PPW * cg) & 31));
-    // read-out: 2 float4 per lane per plane; item i -> row, 4-pixel column chunk
+    const int s0 = choff * 32 + (col ^ ((PPW * cg) & 31));        // this lane's rows: s0 + 32*k
     const int t_in_grp = wq * 32 + lane;
-    int rrow[2], rc4[2], roff[2];
+    int rrow[NRO], rc4[NRO], roff[NRO];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NRO; ++i) {
         const int idx = t_in_grp + i * LPP * 32;
         rrow[i] = idx >> 3;
         rc4[i] = (idx & 7) * 4;
-        roff[i] = rrow[i] * 32 + (rc4[i] ^ ((PPW * (rrow[i] >> 3)) & 31));
+        roff[i] = rrow[i] * 32 + (rc4[i] ^ ((PPW * (rrow[i] / CPT)) & 31));
     }
     const bool vec_ok = ((p.out_sc | p.out_sd) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
-
     const bool fast_rows = vec_ok && grp_base + 32 <= p.HW;      // whole group in range, 16-byte stores
-    auto flush = [&](int buf, int first_plane, int nplanes) {     // tile buffer -> global, 128-byte rows
-        const float* t = tbase + (size_t)buf * TILE;
+
+    // one staged plane (slot tp of tile buffer buf, depth plane `plane`) -> global, as 128-byte rows
+    auto flush_plane = [&](int buf, int tp, int plane) {
+        const float* t = tbase + (size_t)buf * TILE + tp * C * 32;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NRO; ++i) {
             const long long gp = grp_base + rc4[i];
-            float* orow = p.out + (size_t)rrow[i] * p.out_sc + (size_t)(first_plane - p.d_begin) * p.out_sd + gp;
-            const float* ti = t + roff[i];
-            if (fast_rows && nplanes == kTilePlanes) {
-                float4 w[kTilePlanes];
-#pragma unroll
-                for (int tp = 0; tp < kTilePlanes; ++tp) w[tp] = *reinterpret_cast<const float4*>(ti + tp * C * 32);
-#pragma unroll
-                for (int tp = 0; tp < kTilePlanes; ++tp) *reinterpret_cast<float4*>(orow + (size_t)tp * p.out_sd) = w[tp];
+            float* o = p.out + (size_t)rrow[i] * p.out_sc + (size_t)(plane - p.d_begin) * p.out_sd + gp;
+            const float4 w = *reinterpret_cast<const float4*>(t + roff[i]);
+            if (fast_rows) {
+                *reinterpret_cast<float4*>(o) = w;
             } else {
-                for (int tp = 0; tp < nplanes; ++tp) {
-                    const float4 w = *reinterpret_cast<const float4*>(ti + tp * C * 32);
-                    float* o = orow + (size_t)tp * p.out_sd;
-                    if (gp < p.HW) o[0] = w.x;
-                    if (gp + 1 < p.HW) o[1] = w.y;
-                    if (gp + 2 < p.HW) o[2] = w.z;
-                    if (gp + 3 < p.HW) o[3] = w.w;
-                }
+                if (gp < p.HW) o[0] = w.x;
+                if (gp + 1 < p.HW) o[1] = w.y;
+                if (gp + 2 < p.HW) o[2] = w.z;
+                if (gp + 3 < p.HW) o[3] = w.w;
             }
         }
     };
 
+    // Staging protocol: batch b (kTilePlanes planes) is written into tile buffer b&1; the group meets at a
+    // named barrier when the batch is complete; the batch is then drained ONE plane per iteration while
+    // batch b+1 is being computed into the other buffer (no store burst, and the barrier of batch b+1
+    // orders those reads before the buffer is rewritten by batch b+2).
     int staged = 0, batch = 0;                       // planes in the current tile buffer, buffer parity
-    for (int dd = d0; dd < d1; ++dd) {
-        __syncwarp();                                // geo[dd&1] is complete; geo[(dd+1)&1] is free
-        if (dd + 1 < d1) {
-            publish((dd + 1) & 1, dnext);
-            if (dd + 2 < d1) dnext = __ldg(hp + (size_t)(dd + 2) * hyp_stride);
-        }
+    int drain_left = 0, drain_plane = 0;             // planes of the previous batch still to be written out
+
+    // one depth plane; with `ahead`, also this lane's projections for the next pass (table nbuf, planes from nbase)
+    auto process = [&](int dd, const float4 (*gsrc)[PPW], bool ahead, int nbuf, int nbase) {
         float4 g[NV];
         unsigned moved = 0;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
-            g[v] = geo[warp][dd & 1][v][q];
+            g[v] = gsrc[v][q];
             moved |= __float_as_uint(g[v].w) ^ ckey[v];
         }
         if (moved) {                                 // some footprint moved: re-fetch those (in place)
@@ -248,6 +262,9 @@ __global__ void __launch_bounds__(256, 1) sweep_fast_kernel(const SweepParams p)
                 ckey[v] = key;
             }
         }
+
+        float4 gn[KV];
+        if (ahead) project_mine(gn, dnext);
 
         float2 s[NP], sq[NP];
 #pragma unroll
@@ -280,7 +297,8 @@ __global__ void __launch_bounds__(256, 1) sweep_fast_kernel(const SweepParams p)
                 r[j] = __fmul2_rn(w, pinv);                          // sq/V - (sum/V)^2
             }
         }
-        if (LPP == 1) {                              // the warp already owns 32 consecutive pixels
+        if (ahead) store_mine(gn, nbuf, nbase);
+        if (LPP == 1 && CPT == 8) {                  // the warp already owns 32 consecutive pixels
             float* oplane = p.out + (size_t)(dd - p.d_begin) * p.out_sd;
             if (pix_raw < p.HW) {
 #pragma unroll
@@ -296,26 +314,48 @@ __global__ void __launch_bounds__(256, 1) sweep_fast_kernel(const SweepParams p)
                 t[s0 + 64 * j] = r[j].x;
                 t[s0 + 64 * j + 32] = r[j].y;
             }
+            if (drain_left > 0) {                    // previous batch: one plane per iteration
+                flush_plane(batch ^ 1, kTilePlanes - drain_left, drain_plane++);
+                --drain_left;
+            }
             if (++staged == kTilePlanes || dd + 1 == d1) {
                 group_barrier(1 + grp, LPP * 32);
-                flush(batch, dd + 1 - staged, staged);
+                if (dd + 1 == d1) {                  // last batch: nothing left to hide it behind
+                    for (; drain_left > 0; --drain_left)
+                        flush_plane(batch ^ 1, kTilePlanes - drain_left, drain_plane++);
+                    for (int tp = 0; tp < staged; ++tp) flush_plane(batch, tp, dd + 1 - staged + tp);
+                } else {
+                    drain_left = kTilePlanes;
+                    drain_plane = dd + 1 - kTilePlanes;
+                }
                 staged = 0;
                 batch ^= 1;
             }
         }
+    };
+
+    int pass = 0;
+    for (int dd = d0; dd < d1; dd += PB, ++pass) {
+        __syncwarp();                                // table pass&1 is complete; the other one is free
+        process(dd, geo[warp][pass & 1][0], true, (pass + 1) & 1, dd + PB);
+        dnext = depth_of(dd + 2 * PB + po);
+#pragma unroll
+        for (int t = 1; t < PB; ++t)
+            if (dd + t < d1) process(dd + t, geo[warp][pass & 1][t], false, 0, 0);
     }
 }
 
-template <int NV, int LPP>
+template <int CPT, int NV, int LPP>
 constexpr size_t sweep_fast_smem() {
-    return (size_t)8 * 2 * NV * (32 / LPP) * sizeof(float4) +
-           (LPP > 1 ? (size_t)(8 / LPP) * 2 * kTilePlanes * 8 * LPP * 32 * sizeof(float) : 0);
+    constexpr int PB = (LPP >= 2 * NV) ? 2 : 1;
+    return (size_t)8 * 2 * PB * NV * (32 / LPP) * sizeof(float4) +
+           ((LPP == 1 && CPT == 8) ? 0 : (size_t)(8 / LPP) * 2 * kTilePlanes * CPT * LPP * 32 * sizeof(float));
 }
 
-template <int NV, int LPP, int MODE>
+template <int CPT, int NV, int LPP, int MODE>
 int launch_sweep_fast(const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div) {
-    constexpr size_t smem = sweep_fast_smem<NV, LPP>();
-    auto kern = ieee_div ? sweep_fast_kernel<NV, LPP, MODE, true> : sweep_fast_kernel<NV, LPP, MODE, false>;
+    constexpr size_t smem = sweep_fast_smem<CPT, NV, LPP>();
+    auto kern = ieee_div ? sweep_fast_kernel<CPT, NV, LPP, MODE, true> : sweep_fast_kernel<CPT, NV, LPP, MODE, false>;
     static bool configured[2] = {false, false};      // per instantiation, per division flavour
     if (!configured[ieee_div]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -62,7 +62,8 @@ def relative_poses(proj: torch.Tensor) -> torch.Tensor:
     per source view) so the kernel sees bit for bit the matrices the reference sees: a batched matmul
     rounds 1.6 % of the entries differently on B200 (tools/diag_coords.py), which is enough to move
     projected coordinates by an ulp and the cost volume by 1e-4 at production image sizes."""
-    inv = torch.inverse(proj[0:1])
+    # linalg.inv_ex is torch.inverse without the host-side error check (no device->host sync)
+    inv = torch.linalg.inv_ex(proj[0:1], check_errors=False).inverse
     return torch.cat([torch.matmul(proj[i:i + 1], inv) for i in range(1, proj.shape[0])], 0).contiguous()
 
 
