@@ -36,6 +36,7 @@ int sweep_base_group_corr(int cpt, int nv, const SweepParams& p, dim3 grid, cuda
 int sweep_base_weighted_product(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream);
 int sweep_base_pair_mean(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream);
 int sweep_fast_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
+int sweep_lean_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 
 static int sm_count() {
     static int cached = 0;
@@ -142,17 +143,21 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
     };
     dim3 grid;
 
-    // variant 0: production kernel (4 channels per lane where C <= 32, else 8); 3: production kernel with
-    // 8 channels per lane; 2: variant 0 with __fdiv_rn instead of the shared-reciprocal division;
-    // 1: baseline kernel.  Shapes the production kernel is not instantiated for use the baseline.
-    const int variant = a->variant & 15;
+    // variant 0: production kernel (lean formulation, 4 channels per lane where C <= 32, else 8);
+    //         3: the same with 8 channels per lane; 2: variant 0 with __fdiv_rn instead of the shared-reciprocal
+    //         division; 4 / 5: the earlier formulation (sweep_fast.cuh) with 4 / 8 channels per lane; 1: baseline.
+    // Shapes a kernel is not instantiated for fall through to the next one.
+    const int variant = a->variant;
     if (variant != 1 && a->mode == D3D_AGG_VARIANCE && nv <= 4) {
-        int fcpt = (variant == 3 && C % 8 == 0) ? 8 : 4;
+        const bool want8 = (variant == 3 || variant == 5) && C % 8 == 0;
+        int fcpt = want8 ? 8 : 4;
         int fl2 = ilog2_exact(C / fcpt);
         if ((fl2 < 0 || fl2 > 3) && C % 8 == 0) { fcpt = 8; fl2 = ilog2_exact(C / 8); }
         if (fl2 >= 0 && fl2 <= 3) {
             if (int rc = make_grid(fl2, grid)) return rc;
-            int rc = sweep_fast_variance(fcpt, nv, p, grid, stream, variant == 2);
+            int rc = -1;
+            if (variant != 4 && variant != 5) rc = sweep_lean_variance(fcpt, nv, p, grid, stream, variant == 2);
+            if (rc < 0) rc = sweep_fast_variance(fcpt, nv, p, grid, stream, variant == 2);
             if (rc >= 0) return rc;
         }
     }

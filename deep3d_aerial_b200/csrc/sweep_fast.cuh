@@ -36,7 +36,7 @@ namespace d3d {
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 splat(float a) { return make_float2(a, a); }
 
-// key = [31:28] in-bounds mask of the corners nw, ne, sw, se | [27:14] y0+4 | [13:0] x0+4
+// key = [27:14] y0+4 | [13:0] x0+4  (floor corner of the 2x2 footprint)
 constexpr float kMagic = 12582912.f;           // 1.5 * 2^23: float(kMagic + n) has bits 0x4B400000 + n
 constexpr int kMagicBits = 0x4B400000;
 constexpr int kTilePlanes = 8;                 // planes staged per group barrier
@@ -85,13 +85,8 @@ __device__ __forceinline__ float4 project_frac(float rx, float ry, float rz, flo
     if (fx0 > ix) { fx0 -= 1.f; xi -= 1; }
     if (fy0 > iy) { fy0 -= 1.f; yi -= 1; }
     const float fx = __fsub_rn(ix, fx0), fy = __fsub_rn(iy, fy0);
-    const bool x0in = (unsigned)xi < (unsigned)p.W, x1in = (unsigned)(xi + 1) < (unsigned)p.W;
-    const bool y0in = (unsigned)yi < (unsigned)p.H, y1in = (unsigned)(yi + 1) < (unsigned)p.H;
-    unsigned key = ((unsigned)(yi + 4) << 14) | (unsigned)(xi + 4);
-    key |= (x0in && y0in) ? (1u << 28) : 0u;
-    key |= (x1in && y0in) ? (1u << 29) : 0u;
-    key |= (x0in && y1in) ? (1u << 30) : 0u;
-    key |= (x1in && y1in) ? (1u << 31) : 0u;
+    // key: packed floor corner; the re-fetch block derives the in-bounds mask of the four corners from it
+    const unsigned key = ((unsigned)(yi + 4) << 14) | (unsigned)(xi + 4);
     return make_float4(fx, fy, fx * fy, __uint_as_float(key));
 }
 

@@ -190,7 +190,7 @@ CASES = [  # v, c, d, h, w, perpixel
 
 # kernel variants (include/d3d_sweep.h): 0 = production kernel, 1 = baseline kernel, 2 = production kernel
 # with __fdiv_rn instead of the shared-reciprocal division, 3 = production kernel with 8 channels per lane
-VARIANTS = [0, 1, 2, 3]
+VARIANTS = [0, 1, 2, 3, 4, 5]
 
 
 @pytest.mark.parametrize("v,c,d,h,w,perpixel", CASES)
@@ -355,6 +355,7 @@ def test_texel_relayout_round_trip():
 # ------------------------------------------------------------------ (3) properties at full size
 @pytest.mark.parametrize("mode,kw", [(sweep.AGG_VARIANCE, {"variant": 0}), (sweep.AGG_VARIANCE, {"variant": 1}),
                                      (sweep.AGG_VARIANCE, {"variant": 2}), (sweep.AGG_VARIANCE, {"variant": 3}),
+                                     (sweep.AGG_VARIANCE, {"variant": 4}),
                                      (sweep.AGG_GROUP_CORR, {"groups": 8})])
 def test_full_size_config_against_cuda_aten_on_plane_subsets(mode, kw):
     """BASELINE.json configs 2 and 4 (V=5, C=32, D=384, 688x464): the whole volume is built in one launch;
