@@ -19,6 +19,8 @@ static int by_views(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream
 // returns -1 when the shape is not covered (the caller falls back)
 int sweep_lean_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee) {
     if (p.W > 16000 || p.H > 16000) return -1;   // 14-bit corner fields in the footprint key
+    // footprint keys are 32-bit byte offsets into `feats`
+    if ((unsigned long long)(nv + 1) * (unsigned long long)p.HW * (unsigned long long)p.C * 4ull >= (1ull << 32)) return -1;
     if (cpt == 4) {
         switch (p.lpp_log2) {
             case 0: return by_views<4, 1>(nv, p, grid, stream, ieee);

@@ -100,6 +100,107 @@ def block(cpt):
 ''' % (cpt // 2, body, outs)
 
 
+def block_off(cpt):
+    """Offset-keyed re-fetch: the projection producer already turned the footprint into a byte offset, so the
+    common (interior) case is two address adds, four loads and the packed rebuild."""
+    n = 4 * cpt                       # float operands: corner k, channel c -> index k*cpt + c
+    old, key, base, rowb, hwc4, wid, hei, vplus1, texb, texb16 = (n + i for i in range(10))
+    L = []
+    A = L.append
+    A("{")
+    A(".reg .pred p, q, px0, px1, py0, py1;")
+    A(".reg .b32 x0, y0, x1, y1, t, vb, o00, o01, o10, o11;")
+    A(".reg .b64 w, pa, pb, pc, pd, u0, u1, u2, u3;")
+    A("setp.eq.u32 p, %%%d, %%%d;" % (key, old))
+    A("@p bra SAME;")
+    A("mov.u32 %%%d, %%%d;" % (old, key))
+    A("and.b32 t, %%%d, 1;" % key)
+    A("setp.ne.u32 q, t, 0;")
+    A("@q bra SPECIAL;")
+    # interior: key = byte offset (view base included) of the north-west texel; all four corners valid
+    A("cvt.u64.u32 w, %%%d;" % key)
+    A("add.s64 pa, %%%d, w;" % base)
+    A("cvt.u64.u32 w, %%%d;" % rowb)
+    A("add.s64 pc, pa, w;")
+    for k, (ptr, off) in enumerate([("pa", 0), ("pa", 1), ("pc", 0), ("pc", 1)]):
+        for c in range(0, cpt, 4):
+            b = k * cpt + c
+            assert c in (0, 4)
+            if off:
+                o = "+%%%d" % (texb16 if c else texb)
+            else:
+                o = "+16" if c else ""
+            A("ld.global.nc.v4.f32 {%%%d, %%%d, %%%d, %%%d}, [%s%s];" % (b, b + 1, b + 2, b + 3, ptr, o))
+    A("bra REBUILD;")
+    A("SPECIAL:")
+    # border / out of bounds: key = 1 | (x0+4) << 4 | (y0+4) << 18 (key == 1: no corner inside the image);
+    # zeros padding = corners outside the image stay 0 (loads predicated off, so no address is clamped)
+    A("shr.u32 x0, %%%d, 4;" % key)
+    A("and.b32 x0, x0, 0x3fff;")
+    A("sub.s32 x0, x0, 4;")
+    A("shr.u32 y0, %%%d, 18;" % key)
+    A("sub.s32 y0, y0, 4;")
+    A("add.s32 x1, x0, 1;")
+    A("add.s32 y1, y0, 1;")
+    A("setp.lt.u32 px0, x0, %%%d;" % wid)
+    A("setp.lt.u32 px1, x1, %%%d;" % wid)
+    A("setp.lt.u32 py0, y0, %%%d;" % hei)
+    A("setp.lt.u32 py1, y1, %%%d;" % hei)
+    A("mul.lo.u32 vb, %%%d, %%%d;" % (hwc4, vplus1))
+    A("mad.lo.s32 t, y0, %%%d, x0;" % wid)
+    A("mad.lo.s32 o00, t, %%%d, vb;" % texb)
+    A("add.s32 o01, o00, %%%d;" % texb)
+    A("add.s32 o10, o00, %%%d;" % rowb)
+    A("add.s32 o11, o10, %%%d;" % texb)
+    for o, ptr in (("o00", "pa"), ("o01", "pb"), ("o10", "pc"), ("o11", "pd")):
+        A("cvt.u64.u32 w, %s;" % o)
+        A("add.s64 %s, %%%d, w;" % (ptr, base))
+    for i in range(n):
+        A("mov.f32 %%%d, 0f00000000;" % i)
+    for k, (ptr, pxn, pyn) in enumerate([("pa", "px0", "py0"), ("pb", "px1", "py0"), ("pc", "px0", "py1"), ("pd", "px1", "py1")]):
+        A("and.pred q, %s, %s;" % (pxn, pyn))
+        for c in range(0, cpt, 4):
+            b = k * cpt + c
+            o = "" if c == 0 else "+%d" % (4 * c)
+            A("@q ld.global.nc.v4.f32 {%%%d, %%%d, %%%d, %%%d}, [%s%s];" % (b, b + 1, b + 2, b + 3, ptr, o))
+    A("REBUILD:")
+    # A = a, B = b - a, C = c - a, D = (d - c) - (b - a), packed over channel pairs
+    for c in range(0, cpt, 2):
+        a, b, cc, d = c, cpt + c, 2 * cpt + c, 3 * cpt + c
+        for reg, i in (("u0", a), ("u1", b), ("u2", cc), ("u3", d)):
+            A("mov.b64 %s, {%%%d, %%%d};" % (reg, i, i + 1))
+        A("sub.rn.f32x2 u1, u1, u0;")
+        A("sub.rn.f32x2 u3, u3, u2;")
+        A("sub.rn.f32x2 u2, u2, u0;")
+        A("sub.rn.f32x2 u3, u3, u1;")
+        for reg, i in (("u1", b), ("u2", cc), ("u3", d)):
+            A("mov.b64 {%%%d, %%%d}, %s;" % (i, i + 1, reg))
+    A("SAME:")
+    A("}")
+    body = "\n        ".join('"%s\\n\\t"' % x for x in L)
+    ops = []
+    for k in range(4):
+        for j in range(cpt // 2):
+            ops.append('"+f"(t[%d][%d].x)' % (k, j))
+            ops.append('"+f"(t[%d][%d].y)' % (k, j))
+    ops.append('"+r"(cur_key)')
+    outs = ",\n          ".join(", ".join(ops[i:i + 4]) for i in range(0, len(ops), 4))
+    return """// Offset-keyed variant (sweep_lean.cuh): `key` comes from project_off() -- for a footprint whose four corners
+// are inside the image it IS the byte offset of the north-west texel from `base` (view offset included), so
+// the common case is two address adds, four loads and the packed rebuild; border / outside footprints carry
+// their corner instead (bit 0 set) and take the predicated path.  `cur_key` is updated in place.
+template <int VPLUS1, int TEXEL_BYTES>
+__device__ __forceinline__ void refetch_off(float2 (&t)[4][%d], unsigned& cur_key, unsigned key, const float* base,
+                                            unsigned row_bytes, unsigned view_bytes, int width, int height) {
+    asm volatile(
+        %s
+        : %s
+        : "r"(key), "l"(base), "r"(row_bytes), "r"(view_bytes), "r"(width), "r"(height), "n"(VPLUS1),
+          "n"(TEXEL_BYTES), "n"(TEXEL_BYTES + 16));
+}
+""" % (cpt // 2, body, outs)
+
+
 HEADER = '''// GENERATED by tools/gen_refetch.py -- do not edit by hand.
 //
 // refetch_footprint(t, key, old_key, base, W-1, H-1, row_bytes, texel_bytes)
@@ -121,5 +222,5 @@ namespace d3d {
 
 if __name__ == "__main__":
     with open(OUT, "w") as f:
-        f.write(HEADER + block(8) + "\n" + block(4) + "\n}  // namespace d3d\n")
+        f.write(HEADER + block(8) + "\n" + block(4) + "\n" + block_off(8) + "\n" + block_off(4) + "\n}  // namespace d3d\n")
     print("wrote", OUT)
