@@ -147,7 +147,8 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
     //         3: the same with 8 channels per lane; 2: variant 0 with __fdiv_rn instead of the shared-reciprocal
     //         division; 4 / 5: the earlier formulation (sweep_fast.cuh) with 4 / 8 channels per lane; 1: baseline.
     // Shapes a kernel is not instantiated for fall through to the next one.
-    const int variant = a->variant;
+    int variant = a->variant;
+    if (variant >= 16) { p.flags = variant - 16; variant = 0; }   // A/B switches of the production kernel
     if (variant != 1 && a->mode == D3D_AGG_VARIANCE && nv <= 4) {
         const bool want8 = (variant == 3 || variant == 5) && C % 8 == 0;
         int fcpt = want8 ? 8 : 4;

@@ -277,7 +277,9 @@ __global__ void __launch_bounds__(256, (CPT == 4 ? 2 : 1)) sweep_lean_kernel(con
             const float4 w = lds128(dr[i]);
             float* o = optr[i];
             if (fast_rows) {
-                *reinterpret_cast<float4*>(o) = w;
+                // the volume is write-once: keep it out of L1, which holds the texels the re-fetches hit
+                asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(w.x), "f"(w.y),
+                             "f"(w.z), "f"(w.w) : "memory");
             } else {
                 const long long gp = grp_base + ((t_in_grp + i * LPP * 32) & 7) * 4;
                 if (gp < p.HW) o[0] = w.x;
@@ -310,6 +312,16 @@ __global__ void __launch_bounds__(256, (CPT == 4 ? 2 : 1)) sweep_lean_kernel(con
         }
     };
 
+    // The table entries of a plane are loaded right after the arithmetic of the plane before it (their registers
+    // are dead by then), so the move test at the top of a plane never waits on shared memory.
+    float4 g[NV];
+    auto load_table = [&](unsigned base) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) g[v] = lds128(base + v * PPW * 16);
+    };
+    __syncwarp();                                    // table buffer 0 is complete
+    load_table(gr);
+
     int n = 0;
     for (int b0 = d0; b0 < d1; b0 += KT) {
         if (n >= 2) {
@@ -318,16 +330,11 @@ __global__ void __launch_bounds__(256, (CPT == 4 ? 2 : 1)) sweep_lean_kernel(con
         }
 #pragma unroll 1
         for (int t = 0; t < KT; t += PB) {
-            __syncwarp();                            // table `gr` is complete; the other one is free
 #pragma unroll
             for (int tt = 0; tt < PB; ++tt) {
-                float4 g[NV];
                 unsigned moved = 0;
 #pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    g[v] = lds128(gr + tt * GEO_PLANE + v * PPW * 16);
-                    moved |= __float_as_uint(g[v].w) ^ ckey[v];
-                }
+                for (int v = 0; v < NV; ++v) moved |= __float_as_uint(g[v].w) ^ ckey[v];
                 if (moved)                           // some footprint moved: re-fetch those (in place)
                     RefetchAll<NV, C * 4>::run(tex, ckey, g, feats_c, row_bytes, view_bytes, p.W, p.H);
                 float4 gn[KV];
@@ -351,6 +358,19 @@ __global__ void __launch_bounds__(256, (CPT == 4 ? 2 : 1)) sweep_lean_kernel(con
                         }
                     }
                 }
+                if (tt == 0) {
+                    store_mine(gn, gw);
+                    dnext = next_depth();
+                }
+                if (tt + 1 < PB) {
+                    load_table(gr + (tt + 1) * GEO_PLANE);
+                } else {                             // last plane of the pass: swap the table buffers
+                    __syncwarp();                    // the other table is complete; this one is free
+                    gr += gflip;
+                    gw -= gflip;
+                    gflip = 0u - gflip;
+                    load_table(gr);
+                }
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
                     const float2 tneg = __fmul2_rn(s[j], ninv);            // -sum/V
@@ -360,15 +380,8 @@ __global__ void __launch_bounds__(256, (CPT == 4 ? 2 : 1)) sweep_lean_kernel(con
                     sts32(tw + (2 * j + 1) * 128, r.y);
                 }
                 tw += TILE_PLANE;
-                if (tt == 0) {
-                    store_mine(gn, gw);
-                    dnext = next_depth();
-                }
                 if (drain_n > 0) { drain_one(); --drain_n; }
             }
-            gr += gflip;                             // swap the table buffers
-            gw -= gflip;
-            gflip = 0u - gflip;
         }
         // batch n is staged in ring slot slot_c: announce it (one arrival per warp)
         __syncwarp();
