@@ -40,7 +40,7 @@ WORKLOADS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -66,37 +66,87 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples the SM clock and the throttle reasons of one GPU WHILE the timed region runs: NVML in-process
+    every few milliseconds (the timed region of the default run is ~0.3 s, too short for `nvidia-smi -lms`,
+    which needs most of that to start); falls back to nvidia-smi when NVML cannot be loaded."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index = index
-        self.rows = []
+        self.index = self._physical_index(index)
+        self.sm, self.mx, self.seen = [], [], set()
         self.proc = None
+        self.halt = threading.Event()
+        self.how = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
+
+    def _run_nvml(self):
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        bits = {"hw_slowdown": int(getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                "hw_thermal_slowdown": int(getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                "sw_thermal_slowdown": int(getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                "sw_power_cap": int(getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4))}
+        try:
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons
+        except AttributeError:
+            reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        self.how = "nvml"
+        while not self.halt.is_set():
+            self.sm.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.mx.append(int(mx))
+            r = int(reasons(h))
+            for name, bit in bits.items():
+                if r & bit:
+                    self.seen.add(name)
+            time.sleep(0.004)
+
+    def _run_smi(self):
+        self.how = "nvidia-smi"
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits", "-lms", "100"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        for line in self.proc.stdout:
+            r = [x.strip() for x in line.split(",")]
+            if r and r[0].isdigit():
+                self.sm.append(int(r[0]))
+            if len(r) > 1 and r[1].isdigit():
+                self.mx.append(int(r[1]))
+            for i, name in enumerate(self.NAMES):
+                if len(r) > 2 + i and r[2 + i].lower().startswith("active"):
+                    self.seen.add(name)
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
-        except OSError:
-            pass
+            self._run_nvml()
+        except Exception:  # noqa: BLE001 - no NVML binding / driver mismatch: use the CLI
+            try:
+                self._run_smi()
+            except OSError:
+                pass
 
     def stop(self):
+        self.halt.set()
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
-        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": int(statistics.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": [n for n in self.NAMES if n in self.seen], "samples": len(self.sm), "source": self.how}
 
 
 def make_inputs(wl, seed, device):

@@ -100,11 +100,67 @@ def block(cpt):
 ''' % (cpt // 2, body, outs)
 
 
-def block_off(cpt):
+def tex_operands(cpt):
+    ops = []
+    for k in range(4):
+        for j in range(cpt // 2):
+            ops.append('"+f"(t[%d][%d].x)' % (k, j))
+            ops.append('"+f"(t[%d][%d].y)' % (k, j))
+    return ops
+
+
+def rebuild_lines(A, cpt):
+    # A = a, B = b - a, C = c - a, D = (d - c) - (b - a), packed over channel pairs
+    for c in range(0, cpt, 2):
+        a, b, cc, d = c, cpt + c, 2 * cpt + c, 3 * cpt + c
+        for reg, i in (("u0", a), ("u1", b), ("u2", cc), ("u3", d)):
+            A("mov.b64 %s, {%%%d, %%%d};" % (reg, i, i + 1))
+        A("sub.rn.f32x2 u1, u1, u0;")
+        A("sub.rn.f32x2 u3, u3, u2;")
+        A("sub.rn.f32x2 u2, u2, u0;")
+        A("sub.rn.f32x2 u3, u3, u1;")
+        for reg, i in (("u1", b), ("u2", cc), ("u3", d)):
+            A("mov.b64 {%%%d, %%%d}, %s;" % (i, i + 1, reg))
+
+
+def block_rebuild(cpt):
+    n = 4 * cpt
+    mv, vplus1 = n, n + 1
+    L = []
+    A = L.append
+    A("{")
+    A(".reg .pred p;")
+    A(".reg .b32 t;")
+    A(".reg .b64 u0, u1, u2, u3;")
+    A("shr.u32 t, %%%d, %%%d;" % (mv, vplus1))
+    A("and.b32 t, t, 1;")
+    A("setp.eq.u32 p, t, 0;")
+    A("@p bra SAME;")
+    rebuild_lines(A, cpt)
+    A("SAME:")
+    A("}")
+    body = "\n        ".join('"%s\\n\\t"' % x for x in L)
+    ops = tex_operands(cpt)
+    outs = ",\n          ".join(", ".join(ops[i:i + 4]) for i in range(0, len(ops), 4))
+    return """// Split form, second half: corners -> A, B, C, D for the view whose bit is set in `moved`.
+template <int VPLUS1>
+__device__ __forceinline__ void rebuild_off(float2 (&t)[4][%d], unsigned moved) {
+    asm volatile(
+        %s
+        : %s
+        : "r"(moved), "n"(VPLUS1));
+}
+""" % (cpt // 2, body, outs)
+
+
+def block_off(cpt, split=False):
     """Offset-keyed re-fetch: the projection producer already turned the footprint into a byte offset, so the
     common (interior) case is two address adds, four loads and the packed rebuild."""
     n = 4 * cpt                       # float operands: corner k, channel c -> index k*cpt + c
-    old, key, base, rowb, hwc4, wid, hei, vplus1, texb, texb16 = (n + i for i in range(10))
+    if split:
+        old, mv, key, base, rowb, hwc4, wid, hei, vplus1, texb, texb16 = (n + i for i in range(11))
+    else:
+        old, key, base, rowb, hwc4, wid, hei, vplus1, texb, texb16 = (n + i for i in range(10))
     L = []
     A = L.append
     A("{")
@@ -114,6 +170,9 @@ def block_off(cpt):
     A("setp.eq.u32 p, %%%d, %%%d;" % (key, old))
     A("@p bra SAME;")
     A("mov.u32 %%%d, %%%d;" % (old, key))
+    if split:
+        A("shl.b32 t, 1, %%%d;" % vplus1)
+        A("or.b32 %%%d, %%%d, t;" % (mv, mv))
     A("and.b32 t, %%%d, 1;" % key)
     A("setp.ne.u32 q, t, 0;")
     A("@q bra SPECIAL;")
@@ -131,7 +190,7 @@ def block_off(cpt):
             else:
                 o = "+16" if c else ""
             A("ld.global.nc.v4.f32 {%%%d, %%%d, %%%d, %%%d}, [%s%s];" % (b, b + 1, b + 2, b + 3, ptr, o))
-    A("bra REBUILD;")
+    A("bra SAME;" if split else "bra REBUILD;")
     A("SPECIAL:")
     # border / out of bounds: key = 1 | (x0+4) << 4 | (y0+4) << 18 (key == 1: no corner inside the image);
     # zeros padding = corners outside the image stay 0 (loads predicated off, so no address is clamped)
@@ -163,27 +222,32 @@ def block_off(cpt):
             b = k * cpt + c
             o = "" if c == 0 else "+%d" % (4 * c)
             A("@q ld.global.nc.v4.f32 {%%%d, %%%d, %%%d, %%%d}, [%s%s];" % (b, b + 1, b + 2, b + 3, ptr, o))
-    A("REBUILD:")
-    # A = a, B = b - a, C = c - a, D = (d - c) - (b - a), packed over channel pairs
-    for c in range(0, cpt, 2):
-        a, b, cc, d = c, cpt + c, 2 * cpt + c, 3 * cpt + c
-        for reg, i in (("u0", a), ("u1", b), ("u2", cc), ("u3", d)):
-            A("mov.b64 %s, {%%%d, %%%d};" % (reg, i, i + 1))
-        A("sub.rn.f32x2 u1, u1, u0;")
-        A("sub.rn.f32x2 u3, u3, u2;")
-        A("sub.rn.f32x2 u2, u2, u0;")
-        A("sub.rn.f32x2 u3, u3, u1;")
-        for reg, i in (("u1", b), ("u2", cc), ("u3", d)):
-            A("mov.b64 {%%%d, %%%d}, %s;" % (i, i + 1, reg))
+    if not split:
+        A("REBUILD:")
+        rebuild_lines(A, cpt)
     A("SAME:")
     A("}")
     body = "\n        ".join('"%s\\n\\t"' % x for x in L)
-    ops = []
-    for k in range(4):
-        for j in range(cpt // 2):
-            ops.append('"+f"(t[%d][%d].x)' % (k, j))
-            ops.append('"+f"(t[%d][%d].y)' % (k, j))
+    ops = tex_operands(cpt)
     ops.append('"+r"(cur_key)')
+    if split:
+        ops.append('"+r"(moved)')
+        outs = ",\n          ".join(", ".join(ops[i:i + 4]) for i in range(0, len(ops), 4))
+        return """// Split form, first half: when `key` moved, start the loads of the new footprint into the cache registers
+// (raw corners a, b, c, d; corners outside the image = 0), update `cur_key` and set bit VPLUS1 of `moved`.
+// rebuild_off() turns the corners into A, B, C, D once they are needed, so the load latency overlaps whatever
+// the caller puts between the two.
+template <int VPLUS1, int TEXEL_BYTES>
+__device__ __forceinline__ void issue_off(float2 (&t)[4][%d], unsigned& cur_key, unsigned& moved, unsigned key,
+                                          const float* base, unsigned row_bytes, unsigned view_bytes, int width,
+                                          int height) {
+    asm volatile(
+        %s
+        : %s
+        : "r"(key), "l"(base), "r"(row_bytes), "r"(view_bytes), "r"(width), "r"(height), "n"(VPLUS1),
+          "n"(TEXEL_BYTES), "n"(TEXEL_BYTES + 16));
+}
+""" % (cpt // 2, body, outs)
     outs = ",\n          ".join(", ".join(ops[i:i + 4]) for i in range(0, len(ops), 4))
     return """// Offset-keyed variant (sweep_lean.cuh): `key` comes from project_off() -- for a footprint whose four corners
 // are inside the image it IS the byte offset of the north-west texel from `base` (view offset included), so
@@ -222,5 +286,5 @@ namespace d3d {
 
 if __name__ == "__main__":
     with open(OUT, "w") as f:
-        f.write(HEADER + block(8) + "\n" + block(4) + "\n" + block_off(8) + "\n" + block_off(4) + "\n}  // namespace d3d\n")
+        f.write(HEADER + block(8) + "\n" + block(4) + "\n" + block_off(8) + "\n" + block_off(4) + "\n" + block_off(8, True) + "\n" + block_off(4, True) + "\n" + block_rebuild(8) + "\n" + block_rebuild(4) + "\n}  // namespace d3d\n")
     print("wrote", OUT)
