@@ -37,6 +37,7 @@ int sweep_base_weighted_product(int cpt, int nv, const SweepParams& p, dim3 grid
 int sweep_base_pair_mean(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream);
 int sweep_fast_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_lean_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
+int sweep_quad_variance(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 
 static int sm_count() {
     static int cached = 0;
@@ -157,7 +158,9 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
         if (fl2 >= 0 && fl2 <= 3) {
             if (int rc = make_grid(fl2, grid)) return rc;
             int rc = -1;
-            if (variant != 4 && variant != 5) rc = sweep_lean_variance(fcpt, nv, p, grid, stream, variant == 2);
+            // 32-channel features: the four-planes-per-pass kernel (variant 6 keeps the two-plane one for A/B)
+            if ((variant == 0 || variant == 2) && C == 32 && fl2 == 3) rc = sweep_quad_variance(nv, p, grid, stream, variant == 2);
+            if (rc < 0 && variant != 4 && variant != 5) rc = sweep_lean_variance(fcpt, nv, p, grid, stream, variant == 2);
             if (rc < 0) rc = sweep_fast_variance(fcpt, nv, p, grid, stream, variant == 2);
             if (rc >= 0) return rc;
         }

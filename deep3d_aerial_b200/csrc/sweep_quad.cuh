@@ -1,0 +1,343 @@
+// Fused plane sweep, production kernel for 32-channel features -- four planes per projection pass.
+//
+// Decomposition as in sweep_lean.cuh (lane = pixel q of the warp x group cg of 4 channels; 8 lanes share a
+// pixel, a warp owns 4 consecutive reference pixels, the 8 warps of a CTA own 32 pixels = one 128-byte row
+// segment per output channel).  What changed, and why (profiles/ncu_r1l.txt: the FP32 arithmetic of the
+// variance volume is 11.5 of 35 warp instructions per voxel; the projection was 7.9):
+//
+//   * the 8 lanes of a pixel cover one PASS of 4 planes x 4 views with ONE projection chain each: lane cg
+//     projects view cg & 3 for the plane pair cg >> 2, the two planes packed in fp32x2 (FFMA2 / FADD2 / FMUL2,
+//     FADD2.RM for the floor); every operation is the same IEEE operation on each half, so the coordinates stay
+//     bit-identical to the reference chain (project_frac in sweep_fast.cuh);
+//   * the published footprint key is just the floor corner as it falls out of the round-down adds
+//     ((y0 & 0xffff) << 16 | x0 & 0xffff, one PRMT); address arithmetic, the interior test and zeros padding
+//     moved into the re-fetch block (refetch_tok, sweep_refetch.cuh), which runs for ~9 % of the (view, plane)s;
+//   * a pass is also the staged batch: one mbarrier arrive / wait per four planes, no inner pass loop.
+#pragma once
+#include "sweep_lean.cuh"
+
+namespace d3d {
+
+__device__ __forceinline__ float2 lds64(unsigned addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 fadd2_rd(float2 a, float2 b) {       // packed round-down add (FADD2.RM)
+    float2 r;
+    asm("add.rm.f32x2 %0, %1, %2;"
+        : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return r;
+}
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+
+constexpr int kQuadPlanes = 4;       // planes per pass = planes per staged batch
+constexpr int kQuadBuffers = 4;      // staging ring
+
+template <int NV, int V = 0>
+struct RefetchTok {
+    static __device__ __forceinline__ void run(float2 (&tex)[NV][4][2], unsigned (&ckey)[NV], const float4 (&g)[NV],
+                                               const float* base, unsigned row_bytes, int hw, int W, int H) {
+        refetch_tok<V + 1, 128>(tex[V], ckey[V], __float_as_uint(g[V].w), base, row_bytes, hw, W, H);
+        RefetchTok<NV, V + 1>::run(tex, ckey, g, base, row_bytes, hw, W, H);
+    }
+};
+template <int NV>
+struct RefetchTok<NV, NV> {
+    static __device__ __forceinline__ void run(float2 (&)[NV][4][2], unsigned (&)[NV], const float4 (&)[NV], const float*,
+                                               unsigned, int, int, int) {}
+};
+
+template <int NV, bool kIeeeDiv, bool kPerPix>
+__global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p) {
+    constexpr int CPT = 4, LPP = 8, PPW = 4, NP = 2, C = 32;
+    constexpr int KT = kQuadPlanes, NBUF = kQuadBuffers;
+    constexpr unsigned GEO_PLANE = 4 * PPW * 16;           // bytes: one plane's table of one warp (4 view slots)
+    constexpr unsigned GEO_BUF = KT * GEO_PLANE;
+    constexpr unsigned TILE_PLANE = C * 32 * 4;            // bytes: one staged plane
+    constexpr unsigned TILE_BUF = KT * TILE_PLANE;
+    constexpr unsigned TILE_RING = NBUF * TILE_BUF;
+    extern __shared__ float4 smem4[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int cg = lane & 7;
+    const int q = lane >> 3;
+    const int choff = cg * CPT;
+    const long long grp_base = (long long)blockIdx.x * 32;
+
+    const int d0 = p.d_begin + blockIdx.y * p.d_chunk;
+    const int d1 = min(d0 + p.d_chunk, p.d_end);
+    if (d0 >= d1) return;
+
+    // ---- shared-memory map (bytes): mbarriers | projection tables | staging ring | hypotheses
+    const unsigned bar0 = smem_u32(smem4);
+    const unsigned sm0 = bar0 + 64;
+    const unsigned geo_w = sm0 + warp * 2 * GEO_BUF;
+    const unsigned tile_g = sm0 + 8 * 2 * GEO_BUF;
+    const unsigned hyp_s = tile_g + TILE_RING;
+
+    if (threadIdx.x < NBUF) mbar_init(bar0 + threadIdx.x * 8, 8);      // one arrival per warp
+    if (!kPerPix) {                                        // fronto-parallel sweep: stage the chunk's depths
+        const int n = d1 - d0 + kLeanHypPad;
+        for (int i = threadIdx.x; i < n; i += 256) sts32(hyp_s + i * 4, __ldg(p.hyps + min(d0 + i, d1 - 1)));
+    }
+    __syncthreads();
+
+    // ---- this lane's projection job: view cg & 3, planes 2*(cg >> 2) and +1 of every pass
+    const int pv = min(cg & 3, NV - 1);
+    const int pp = cg >> 2;
+    const bool owner = (cg & 3) < NV;
+    float rx, ry, rz, tx, ty, tz;
+    float2 rf[NP];
+    const float* hp = p.hyps;                              // kPerPix: this pixel's hypotheses, first plane of the job
+    {
+        const long long pix_raw = grp_base + warp * PPW + q;
+        const int pix = pix_raw < p.HW ? (int)pix_raw : p.HW - 1;    // clamp: the warp stays whole
+        const int py = pix / p.W, px = pix - py * p.W;
+        const float* m = p.pose + pv * 16;
+        rx = fmaf(m[2], 1.f, fmaf(m[1], (float)py, m[0] * (float)px));
+        ry = fmaf(m[6], 1.f, fmaf(m[5], (float)py, m[4] * (float)px));
+        rz = fmaf(m[10], 1.f, fmaf(m[9], (float)py, m[8] * (float)px));
+        tx = m[3]; ty = m[7]; tz = m[11];
+        const float4 w = ldg4(p.feats + (size_t)pix * C + choff);
+        rf[0] = f2(w.x, w.y);
+        rf[1] = f2(w.z, w.w);
+        if (kPerPix) hp = p.hyps + (size_t)pix + (size_t)(d0 + 2 * pp) * p.HW;
+    }
+
+    float2 tex[NV][4][NP];      // per view: A, B, C, D of the current 2x2 footprint
+    unsigned ckey[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        ckey[v] = 0x7fff7fffu;  // no footprint has this corner
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < NP; ++j) tex[v][k][j] = f2(0.f, 0.f);
+    }
+    const float* feats_c = p.feats + choff;
+    const unsigned row_bytes = (unsigned)p.W * (unsigned)(C * 4);
+
+    // ---- running shared-memory addresses
+    unsigned gr = geo_w + q * 16;                                          // read: + t*GEO_PLANE + v*PPW*16
+    unsigned gw = geo_w + GEO_BUF + 2 * pp * GEO_PLANE + pv * PPW * 16 + q * 16;   // write (other buffer)
+    unsigned gflip = GEO_BUF;                                              // +/- distance between the buffers
+    unsigned tw = tile_g + (choff * 32 + ((warp * PPW + q) ^ ((PPW * cg) & 31))) * 4;   // + k*128 per channel row
+    unsigned dr;                                           // drain: staged row chunk this lane moves
+    float* optr;                                           // drain: where it goes
+    {
+        const int row = threadIdx.x >> 3, c4 = (threadIdx.x & 7) * 4;
+        dr = tile_g + (row * 32 + (c4 ^ ((PPW * (row / CPT)) & 31))) * 4;
+        optr = p.out + ((long long)row * p.out_sc + (long long)(d0 - p.d_begin) * p.out_sd + grp_base + c4);
+        // H*W is a multiple of 32 (checked by the launcher): every CTA owns a whole row segment
+    }
+
+    // ---- hypotheses of the two planes this lane projects in the next pass
+    unsigned hs = hyp_s + 2 * pp * 4;                      // !kPerPix: running shared-memory address
+    int hplane = d0 + 2 * pp;                              // kPerPix: plane `hp` points at
+    auto next_depths = [&]() -> float2 {
+        float2 d;
+        if (kPerPix) {
+            const size_t hw = (size_t)p.HW;
+            const float* a = hplane < d1 ? hp : hp - (size_t)(hplane - (d1 - 1)) * hw;
+            const float* b = hplane + 1 < d1 ? hp + hw : a;
+            d = f2(__ldg(a), __ldg(b));
+            hp += (size_t)KT * hw;
+            hplane += KT;
+        } else {
+            d = lds64(hs);
+            hs += KT * 4;
+        }
+        return d;
+    };
+
+    // Packed projection of the lane's view at two depths; every packed operation is the reference's IEEE
+    // operation on each half (see project_frac in sweep_fast.cuh for the order and why it is that order).
+    auto project2 = [&](float2 d, float4& ea, float4& eb) {
+        // (nvcc contracts __fmul2_rn + __fadd2_rn into one FFMA2, which would round once where the reference
+        // rounds twice: every add that follows a multiply is a scalar __fadd_rn)
+        const float2 Xm = __fmul2_rn(splat(rx), d), Ym = __fmul2_rn(splat(ry), d), Zm = __fmul2_rn(splat(rz), d);
+        const float2 X = f2(__fadd_rn(Xm.x, tx), __fadd_rn(Xm.y, tx));
+        const float2 Y = f2(__fadd_rn(Ym.x, ty), __fadd_rn(Ym.y, ty));
+        const float2 Z = f2(__fadd_rn(Zm.x, tz), __fadd_rn(Zm.y, tz));
+        float2 u, v;
+        if (kIeeeDiv) {
+            u = f2(__fdiv_rn(X.x, Z.x), __fdiv_rn(X.y, Z.y));
+            v = f2(__fdiv_rn(Y.x, Z.x), __fdiv_rn(Y.y, Z.y));
+        } else {                                           // div2() of sweep_fast.cuh, both planes at once
+            float2 r;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(Z.x));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(Z.y));
+            const float2 nZ = neg2(Z);
+            r = __ffma2_rn(__ffma2_rn(nZ, r, splat(1.f)), r, r);
+            const float2 qu = __fmul2_rn(X, r), qv = __fmul2_rn(Y, r);
+            u = __ffma2_rn(__ffma2_rn(nZ, qu, X), r, qu);
+            v = __ffma2_rn(__ffma2_rn(nZ, qv, Y), r, qv);
+        }
+        float2 ix = __fmul2_rn(u, splat(p.inv_half_w));
+        float2 iy = __fmul2_rn(v, splat(p.inv_half_h));
+        ix = f2(__fsub_rn(ix.x, 1.f), __fsub_rn(ix.y, 1.f));
+        iy = f2(__fsub_rn(iy.x, 1.f), __fsub_rn(iy.y, 1.f));
+        ix = __fadd2_rn(ix, splat(1.f));
+        iy = __fadd2_rn(iy, splat(1.f));
+        ix = __fmul2_rn(ix, splat(0.5f));
+        iy = __fmul2_rn(iy, splat(0.5f));
+        ix = __fmul2_rn(ix, splat(p.wm1));
+        iy = __fmul2_rn(iy, splat(p.hm1));
+        const float xhi = p.wm1 + 2.f, yhi = p.hm1 + 2.f;
+        ix = f2(fminf(fmaxf(ix.x, -2.f), xhi), fminf(fmaxf(ix.y, -2.f), xhi));   // NaN -> -2: out of bounds
+        iy = f2(fminf(fmaxf(iy.x, -2.f), yhi), fminf(fmaxf(iy.y, -2.f), yhi));
+        // floor: a round-down add against 1.5*2^23 leaves floor() in the low mantissa bits, exactly
+        const float2 mx = fadd2_rd(ix, splat(kMagic)), my = fadd2_rd(iy, splat(kMagic));
+        const float2 fx = __fadd2_rn(ix, neg2(__fadd2_rn(mx, splat(-kMagic))));
+        const float2 fy = __fadd2_rn(iy, neg2(__fadd2_rn(my, splat(-kMagic))));
+        const float2 fxy = __fmul2_rn(fx, fy);
+        const unsigned ka = __byte_perm(__float_as_uint(mx.x), __float_as_uint(my.x), 0x5410);
+        const unsigned kb = __byte_perm(__float_as_uint(mx.y), __float_as_uint(my.y), 0x5410);
+        ea = make_float4(fx.x, fy.x, fxy.x, __uint_as_float(ka));
+        eb = make_float4(fx.y, fy.y, fxy.y, __uint_as_float(kb));
+    };
+
+    // ---- prologue: projections of the first pass into table buffer 0
+    {
+        float4 ea, eb;
+        project2(next_depths(), ea, eb);
+        if (owner) {
+            sts128(gw - GEO_BUF, ea);
+            sts128(gw - GEO_BUF + GEO_PLANE, eb);
+        }
+    }
+    float2 dnext = next_depths();
+
+    const float invV = 1.f / (float)(NV + 1);
+    const float2 ninv = splat(-invV), pinv = splat(invV);
+
+    // Staging protocol (see sweep_lean.cuh): batch n is computed into ring slot n % NBUF and drained, one plane
+    // per iteration, while batch n+2 is computed; the drain pointers simply keep running.
+    unsigned bar_c = bar0, bar_d = bar0, par_d = 0;
+    int slot_c = 0, slot_d = 0;
+
+    auto drain_one = [&]() {
+        const float4 w = lds128(dr);
+        dr += TILE_PLANE;
+        // the volume is write-once: keep it out of L1, which holds the texels the re-fetches hit
+        asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(optr), "f"(w.x), "f"(w.y),
+                     "f"(w.z), "f"(w.w) : "memory");
+        optr += p.out_sd;
+    };
+    auto begin_drain = [&]() {
+        mbar_wait(bar_d, par_d);
+        bar_d += 8;
+        if (++slot_d == NBUF) { slot_d = 0; bar_d = bar0; par_d ^= 1; }
+    };
+
+    float4 g[NV];
+    auto load_table = [&](unsigned base) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) g[v] = lds128(base + v * PPW * 16);
+    };
+    __syncwarp();                                    // table buffer 0 is complete
+    load_table(gr);
+
+    int n = 0;
+#pragma unroll 1
+    for (int b0 = d0; b0 < d1; b0 += KT, ++n) {
+        const bool draining = n >= 2;                // every batch but the last is full
+        if (draining) begin_drain();
+#pragma unroll
+        for (int t = 0; t < KT; ++t) {
+            unsigned moved = 0;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) moved |= __float_as_uint(g[v].w) ^ ckey[v];
+            if (moved)                               // some footprint moved: re-fetch those (in place)
+                RefetchTok<NV>::run(tex, ckey, g, feats_c, row_bytes, p.HW, p.W, p.H);
+            float4 ea, eb;
+            if (t == 0) project2(dnext, ea, eb);     // next pass, interleaved with the arithmetic
+
+            float2 s[NP], sq[NP];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const float2 fx = splat(g[v].x), fy = splat(g[v].y), fxy = splat(g[v].z);
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    float2 o = __ffma2_rn(fx, tex[v][1][j], tex[v][0][j]);
+                    o = __ffma2_rn(fy, tex[v][2][j], o);
+                    o = __ffma2_rn(fxy, tex[v][3][j], o);
+                    if (v == 0) {
+                        s[j] = __fadd2_rn(rf[j], o);
+                        sq[j] = __ffma2_rn(o, o, __fmul2_rn(rf[j], rf[j]));
+                    } else {
+                        s[j] = __fadd2_rn(s[j], o);
+                        sq[j] = __ffma2_rn(o, o, sq[j]);
+                    }
+                }
+            }
+            if (t == 0) {
+                if (owner) {
+                    sts128(gw, ea);
+                    sts128(gw + GEO_PLANE, eb);
+                }
+                dnext = next_depths();
+            }
+            if (t + 1 < KT) {
+                load_table(gr + (t + 1) * GEO_PLANE);
+            } else {                                 // last plane of the pass: swap the table buffers
+                __syncwarp();                        // the other table is complete; this one is free
+                gr += gflip;
+                gw -= gflip;
+                gflip = 0u - gflip;
+                load_table(gr);
+            }
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                const float2 tneg = __fmul2_rn(s[j], ninv);            // -sum/V
+                const float2 w = __ffma2_rn(tneg, s[j], sq[j]);        // sq - sum^2/V
+                const float2 r = __fmul2_rn(w, pinv);                  // sq/V - (sum/V)^2
+                sts32(tw + (2 * j) * 128 + t * TILE_PLANE, r.x);
+                sts32(tw + (2 * j + 1) * 128 + t * TILE_PLANE, r.y);
+            }
+            if (draining) drain_one();
+        }
+        // batch n is staged in ring slot slot_c: announce it (one arrival per warp)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_c);
+        bar_c += 8;
+        tw += TILE_BUF;
+        if (++slot_c == NBUF) { slot_c = 0; bar_c = bar0; tw -= TILE_RING; }
+        if (draining && slot_d == 0) dr -= TILE_RING;   // the drained slot was the last of the ring
+    }
+    // the sweep is over: the last two batches have nothing left to hide behind
+    for (int m = max(n - 2, 0); m < n; ++m) {
+        begin_drain();
+        for (int k = min(KT, d1 - (d0 + m * KT)); k > 0; --k) drain_one();
+        if (slot_d == 0) dr -= TILE_RING;
+    }
+}
+
+template <int NV>
+int launch_sweep_quad(const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div) {
+    const size_t smem = 64 + (size_t)8 * 2 * kQuadPlanes * 4 * 4 * 16 + (size_t)kQuadBuffers * kQuadPlanes * 32 * 32 * 4 +
+                        (p.perpix ? 0 : (size_t)(p.d_chunk + kLeanHypPad) * 4);
+    if (smem > 110 * 1024) return -1;                // keep two CTAs per SM; absurd depth chunks go elsewhere
+    void (*kern)(const SweepParams);
+    const int which = (ieee_div ? 2 : 0) + (p.perpix ? 1 : 0);
+    switch (which) {
+        case 0: kern = sweep_quad_kernel<NV, false, false>; break;
+        case 1: kern = sweep_quad_kernel<NV, false, true>; break;
+        case 2: kern = sweep_quad_kernel<NV, true, false>; break;
+        default: kern = sweep_quad_kernel<NV, true, true>; break;
+    }
+    static size_t configured[4] = {0, 0, 0, 0};
+    if (configured[which] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(D3D_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+        configured[which] = smem;
+    }
+    kern<<<grid, 256, smem, stream>>>(p);
+    count_launch();
+    return check_launch("sweep_quad_kernel");
+}
+
+}  // namespace d3d

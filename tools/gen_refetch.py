@@ -265,6 +265,84 @@ __device__ __forceinline__ void refetch_off(float2 (&t)[4][%d], unsigned& cur_ke
 """ % (cpt // 2, body, outs)
 
 
+def block_tok(cpt):
+    """Token-keyed re-fetch (sweep_quad.cuh): the projecting lane publishes only the packed floor corner
+    (low 16 bits of the two round-down-add results); address and border handling live here, on the rare path."""
+    n = 4 * cpt
+    old, key, base, rowb, hw, wid, hei, wm1, hm1, vplus1, texb, texb16 = (n + i for i in range(12))
+    L = []
+    A = L.append
+    A("{")
+    A(".reg .pred p, q, r, px0, px1, py0, py1;")
+    A(".reg .b32 x0, y0, x1, y1, t;")
+    A(".reg .b64 w, pa, pc, u0, u1, u2, u3;")
+    A("setp.eq.u32 p, %%%d, %%%d;" % (key, old))
+    A("@p bra SAME;")
+    A("mov.u32 %%%d, %%%d;" % (old, key))
+    A("bfe.s32 x0, %%%d, 0, 16;" % key)
+    A("bfe.s32 y0, %%%d, 16, 16;" % key)
+    A("mad.lo.s32 t, y0, %%%d, x0;" % wid)
+    A("mad.lo.s32 t, %%%d, %%%d, t;" % (hw, vplus1))
+    A("mad.wide.s32 pa, t, %%%d, %%%d;" % (texb, base))
+    A("cvt.u64.u32 w, %%%d;" % rowb)
+    A("add.s64 pc, pa, w;")
+    A("setp.lt.u32 q, x0, %%%d;" % wm1)
+    A("setp.lt.u32 r, y0, %%%d;" % hm1)
+    A("and.pred q, q, r;")
+    A("@!q bra SPECIAL;")
+    for k, (ptr, off) in enumerate([("pa", 0), ("pa", 1), ("pc", 0), ("pc", 1)]):
+        for c in range(0, cpt, 4):
+            b = k * cpt + c
+            assert c in (0, 4)
+            if off:
+                o = "+%%%d" % (texb16 if c else texb)
+            else:
+                o = "+16" if c else ""
+            A("ld.global.nc.v4.f32 {%%%d, %%%d, %%%d, %%%d}, [%s%s];" % (b, b + 1, b + 2, b + 3, ptr, o))
+    A("bra REBUILD;")
+    A("SPECIAL:")
+    # zeros padding: corners outside the image stay 0 (loads predicated off, nothing is clamped)
+    A("add.s32 x1, x0, 1;")
+    A("add.s32 y1, y0, 1;")
+    A("setp.lt.u32 px0, x0, %%%d;" % wid)
+    A("setp.lt.u32 px1, x1, %%%d;" % wid)
+    A("setp.lt.u32 py0, y0, %%%d;" % hei)
+    A("setp.lt.u32 py1, y1, %%%d;" % hei)
+    for i in range(n):
+        A("mov.f32 %%%d, 0f00000000;" % i)
+    for k, (ptr, off, pxn, pyn) in enumerate([("pa", 0, "px0", "py0"), ("pa", 1, "px1", "py0"), ("pc", 0, "px0", "py1"), ("pc", 1, "px1", "py1")]):
+        A("and.pred q, %s, %s;" % (pxn, pyn))
+        for c in range(0, cpt, 4):
+            b = k * cpt + c
+            if off:
+                o = "+%%%d" % (texb16 if c else texb)
+            else:
+                o = "+16" if c else ""
+            A("@q ld.global.nc.v4.f32 {%%%d, %%%d, %%%d, %%%d}, [%s%s];" % (b, b + 1, b + 2, b + 3, ptr, o))
+    A("REBUILD:")
+    rebuild_lines(A, cpt)
+    A("SAME:")
+    A("}")
+    body = "\n        ".join('"%s\\n\\t"' % x for x in L)
+    ops = tex_operands(cpt)
+    ops.append('"+r"(cur_key)')
+    outs = ",\n          ".join(", ".join(ops[i:i + 4]) for i in range(0, len(ops), 4))
+    return """// Token-keyed variant (sweep_quad.cuh): `key` = (y0 & 0xffff) << 16 | (x0 & 0xffff), the floor corner of the
+// footprint as it falls out of the round-down adds of the projection.  Everything else -- the texel address
+// (64-bit: no size limit on `feats`), the interior test, zeros padding at the border (loads predicated off) and
+// the rebuild of A, B, C, D -- happens here, on the rare path.  `cur_key` is updated in place.
+template <int VPLUS1, int TEXEL_BYTES>
+__device__ __forceinline__ void refetch_tok(float2 (&t)[4][%d], unsigned& cur_key, unsigned key, const float* base,
+                                            unsigned row_bytes, int hw, int width, int height) {
+    asm volatile(
+        %s
+        : %s
+        : "r"(key), "l"(base), "r"(row_bytes), "r"(hw), "r"(width), "r"(height), "r"(width - 1), "r"(height - 1),
+          "n"(VPLUS1), "n"(TEXEL_BYTES), "n"(TEXEL_BYTES + 16));
+}
+""" % (cpt // 2, body, outs)
+
+
 HEADER = '''// GENERATED by tools/gen_refetch.py -- do not edit by hand.
 //
 // refetch_footprint(t, key, old_key, base, W-1, H-1, row_bytes, texel_bytes)
@@ -286,5 +364,5 @@ namespace d3d {
 
 if __name__ == "__main__":
     with open(OUT, "w") as f:
-        f.write(HEADER + block(8) + "\n" + block(4) + "\n" + block_off(8) + "\n" + block_off(4) + "\n" + block_off(8, True) + "\n" + block_off(4, True) + "\n" + block_rebuild(8) + "\n" + block_rebuild(4) + "\n}  // namespace d3d\n")
+        f.write(HEADER + block(8) + "\n" + block(4) + "\n" + block_off(8) + "\n" + block_off(4) + "\n" + block_off(8, True) + "\n" + block_off(4, True) + "\n" + block_rebuild(8) + "\n" + block_rebuild(4) + "\n" + block_tok(4) + "\n}  // namespace d3d\n")
     print("wrote", OUT)
