@@ -38,6 +38,8 @@ int sweep_base_pair_mean(int cpt, int nv, const SweepParams& p, dim3 grid, cudaS
 int sweep_fast_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_lean_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_quad_variance(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
+int sweep_quad_group_corr(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
+int sweep_quad_weighted_product(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 
 static int sm_count() {
     static int cached = 0;
@@ -164,6 +166,15 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
             if (rc < 0) rc = sweep_fast_variance(fcpt, nv, p, grid, stream, variant == 2);
             if (rc >= 0) return rc;
         }
+    }
+    // 32-channel features, <= 4 source views: the four-planes-per-pass kernel also builds the group-wise
+    // correlation and the weighted-product volumes
+    if ((variant == 0 || variant == 2) && C == 32 && nv <= 4 &&
+        (a->mode == D3D_AGG_GROUP_CORR || a->mode == D3D_AGG_WEIGHTED_PRODUCT)) {
+        if (int rc = make_grid(3, grid)) return rc;
+        const int rc = a->mode == D3D_AGG_GROUP_CORR ? sweep_quad_group_corr(nv, p, grid, stream, variant == 2)
+                                                     : sweep_quad_weighted_product(nv, p, grid, stream, variant == 2);
+        if (rc >= 0) return rc;
     }
     if (int rc = make_grid(lpp_log2, grid)) return rc;
     switch (a->mode) {

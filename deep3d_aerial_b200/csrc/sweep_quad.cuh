@@ -49,7 +49,10 @@ struct RefetchTok<NV, NV> {
                                                unsigned, int, int, int) {}
 };
 
-template <int NV, bool kIeeeDiv, bool kPerPix>
+// MODE: D3D_AGG_VARIANCE, D3D_AGG_WEIGHTED_PRODUCT (both write C rows per plane) or D3D_AGG_GROUP_CORR
+// (p.groups rows; a lane's 4 channels are whole groups, one group, or a slice of a group that spans lanes).
+// GS: channels per group known at compile time (4 = the G=8 configuration of BASELINE.json), 0 = read p.groups.
+template <int NV, int MODE, bool kIeeeDiv, bool kPerPix, int GS = 0>
 __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p) {
     constexpr int CPT = 4, LPP = 8, PPW = 4, NP = 2, C = 32;
     constexpr int KT = kQuadPlanes, NBUF = kQuadBuffers;
@@ -124,15 +127,39 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
     unsigned gr = geo_w + q * 16;                                          // read: + t*GEO_PLANE + v*PPW*16
     unsigned gw = geo_w + GEO_BUF + 2 * pp * GEO_PLANE + pv * PPW * 16 + q * 16;   // write (other buffer)
     unsigned gflip = GEO_BUF;                                              // +/- distance between the buffers
-    unsigned tw = tile_g + (choff * 32 + ((warp * PPW + q) ^ ((PPW * cg) & 31))) * 4;   // + k*128 per channel row
+    // output rows of this lane: variance / weighted product / groups of 1 channel: its 4 channels; groups of 2:
+    // two rows; wider groups: one row, written by the first lane of the group.  Row r of a staged plane is
+    // swizzled by the lane that owns it (4 * (r / rows per lane)), which keeps the staging stores conflict free
+    // and every aligned run of 4 pixels contiguous for the 16-byte read-out.
+    const int gs = (MODE != D3D_AGG_GROUP_CORR) ? 1 : (GS ? GS : C / p.groups);   // channels per output row
+    const int rpl_log2 = gs >= 4 ? 0 : (gs == 2 ? 1 : 2);                  // log2(rows per lane)
+    const int row0 = gs >= 4 ? choff / gs : (choff >> (gs == 2 ? 1 : 0));  // this lane's first row
+    const int n_rows = (MODE == D3D_AGG_GROUP_CORR) ? p.groups : C;
+    unsigned tw = tile_g + (row0 * 32 + ((warp * PPW + q) ^ ((4 * (row0 >> rpl_log2)) & 31))) * 4;   // + k*128 per row
     unsigned dr;                                           // drain: staged row chunk this lane moves
     float* optr;                                           // drain: where it goes
+    bool drain_row;                                        // fewer than 32 rows (group-wise correlation)
     {
         const int row = threadIdx.x >> 3, c4 = (threadIdx.x & 7) * 4;
-        dr = tile_g + (row * 32 + (c4 ^ ((PPW * (row / CPT)) & 31))) * 4;
+        dr = tile_g + (row * 32 + (c4 ^ ((4 * (row >> rpl_log2)) & 31))) * 4;
         optr = p.out + ((long long)row * p.out_sc + (long long)(d0 - p.d_begin) * p.out_sd + grp_base + c4);
+        drain_row = row < n_rows;
         // H*W is a multiple of 32 (checked by the launcher): every CTA owns a whole row segment
     }
+    float wt[NV];                                          // weighted product: this pixel's view weights
+    float winv = 0.f;
+    if (MODE == D3D_AGG_WEIGHTED_PRODUCT) {
+        const long long pix_raw = grp_base + warp * PPW + q;
+        const int pix = pix_raw < p.HW ? (int)pix_raw : p.HW - 1;
+        float wsum = p.eps_num ? 0.f : 1e-5f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            wt[v] = __ldg(p.weights + (size_t)v * p.HW + pix);
+            wsum += wt[v];                                 // adamvs.py:494,506 accumulation order
+        }
+        winv = __frcp_rn(wsum);
+    }
+    const float gscale = 1.f / ((float)gs * (float)NV);    // group-wise correlation: mean over group and views
 
     // ---- hypotheses of the two planes this lane projects in the next pass
     unsigned hs = hyp_s + 2 * pp * 4;                      // !kPerPix: running shared-memory address
@@ -223,8 +250,9 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
         const float4 w = lds128(dr);
         dr += TILE_PLANE;
         // the volume is write-once: keep it out of L1, which holds the texels the re-fetches hit
-        asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(optr), "f"(w.x), "f"(w.y),
-                     "f"(w.z), "f"(w.w) : "memory");
+        if (MODE != D3D_AGG_GROUP_CORR || drain_row)
+            asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(optr), "f"(w.x), "f"(w.y),
+                         "f"(w.z), "f"(w.w) : "memory");
         optr += p.out_sd;
     };
     auto begin_drain = [&]() {
@@ -256,7 +284,7 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
             float4 ea, eb;
             if (t == 0) project2(dnext, ea, eb);     // next pass, interleaved with the arithmetic
 
-            float2 s[NP], sq[NP];
+            float2 s[NP], sq[NP];                    // variance: sum, sum of squares; otherwise s = accumulator
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
                 const float2 fx = splat(g[v].x), fy = splat(g[v].y), fxy = splat(g[v].z);
@@ -265,12 +293,19 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
                     float2 o = __ffma2_rn(fx, tex[v][1][j], tex[v][0][j]);
                     o = __ffma2_rn(fy, tex[v][2][j], o);
                     o = __ffma2_rn(fxy, tex[v][3][j], o);
-                    if (v == 0) {
-                        s[j] = __fadd2_rn(rf[j], o);
-                        sq[j] = __ffma2_rn(o, o, __fmul2_rn(rf[j], rf[j]));
-                    } else {
-                        s[j] = __fadd2_rn(s[j], o);
-                        sq[j] = __ffma2_rn(o, o, sq[j]);
+                    if (MODE == D3D_AGG_VARIANCE) {
+                        if (v == 0) {
+                            s[j] = __fadd2_rn(rf[j], o);
+                            sq[j] = __ffma2_rn(o, o, __fmul2_rn(rf[j], rf[j]));
+                        } else {
+                            s[j] = __fadd2_rn(s[j], o);
+                            sq[j] = __ffma2_rn(o, o, sq[j]);
+                        }
+                    } else if (MODE == D3D_AGG_GROUP_CORR) {           // sum_v ref * warped_v
+                        s[j] = (v == 0) ? __fmul2_rn(rf[j], o) : __ffma2_rn(rf[j], o, s[j]);
+                    } else {                                           // sum_v (warped_v * ref) * weight_v
+                        s[j] = __ffma2_rn(__fmul2_rn(o, rf[j]), splat(wt[v]),
+                                          v == 0 ? splat(p.eps_num ? 1e-5f : 0.f) : s[j]);
                     }
                 }
             }
@@ -290,13 +325,37 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
                 gflip = 0u - gflip;
                 load_table(gr);
             }
+            if (MODE == D3D_AGG_VARIANCE) {
 #pragma unroll
-            for (int j = 0; j < NP; ++j) {
-                const float2 tneg = __fmul2_rn(s[j], ninv);            // -sum/V
-                const float2 w = __ffma2_rn(tneg, s[j], sq[j]);        // sq - sum^2/V
-                const float2 r = __fmul2_rn(w, pinv);                  // sq/V - (sum/V)^2
-                sts32(tw + (2 * j) * 128 + t * TILE_PLANE, r.x);
-                sts32(tw + (2 * j + 1) * 128 + t * TILE_PLANE, r.y);
+                for (int j = 0; j < NP; ++j) {
+                    const float2 tneg = __fmul2_rn(s[j], ninv);            // -sum/V
+                    const float2 w = __ffma2_rn(tneg, s[j], sq[j]);        // sq - sum^2/V
+                    const float2 r = __fmul2_rn(w, pinv);                  // sq/V - (sum/V)^2
+                    sts32(tw + (2 * j) * 128 + t * TILE_PLANE, r.x);
+                    sts32(tw + (2 * j + 1) * 128 + t * TILE_PLANE, r.y);
+                }
+            } else if (MODE == D3D_AGG_WEIGHTED_PRODUCT) {
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    const float2 r = __fmul2_rn(s[j], splat(winv));
+                    sts32(tw + (2 * j) * 128 + t * TILE_PLANE, r.x);
+                    sts32(tw + (2 * j + 1) * 128 + t * TILE_PLANE, r.y);
+                }
+            } else {                                 // group-wise correlation: mean over the group and the views
+                if (gs == 1) {
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) {
+                        sts32(tw + (2 * j) * 128 + t * TILE_PLANE, s[j].x * gscale);
+                        sts32(tw + (2 * j + 1) * 128 + t * TILE_PLANE, s[j].y * gscale);
+                    }
+                } else if (gs == 2) {
+                    sts32(tw + t * TILE_PLANE, (0.f + s[0].x + s[0].y) * gscale);
+                    sts32(tw + 128 + t * TILE_PLANE, (0.f + s[1].x + s[1].y) * gscale);
+                } else {
+                    float a = ((s[0].x + s[0].y) + s[1].x) + s[1].y;       // the lane's 4 channels, in order
+                    for (int o = 1; o < gs / 4; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    if ((cg & (gs / 4 - 1)) == 0) sts32(tw + t * TILE_PLANE, a * gscale);
+                }
             }
             if (draining) drain_one();
         }
@@ -316,20 +375,22 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
     }
 }
 
-template <int NV>
+template <int NV, int MODE>
 int launch_sweep_quad(const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div) {
     const size_t smem = 64 + (size_t)8 * 2 * kQuadPlanes * 4 * 4 * 16 + (size_t)kQuadBuffers * kQuadPlanes * 32 * 32 * 4 +
                         (p.perpix ? 0 : (size_t)(p.d_chunk + kLeanHypPad) * 4);
     if (smem > 110 * 1024) return -1;                // keep two CTAs per SM; absurd depth chunks go elsewhere
     void (*kern)(const SweepParams);
     const int which = (ieee_div ? 2 : 0) + (p.perpix ? 1 : 0);
+    const bool g8 = MODE == D3D_AGG_GROUP_CORR && p.groups == 8 && !ieee_div;     // groups of 4 channels = one lane
     switch (which) {
-        case 0: kern = sweep_quad_kernel<NV, false, false>; break;
-        case 1: kern = sweep_quad_kernel<NV, false, true>; break;
-        case 2: kern = sweep_quad_kernel<NV, true, false>; break;
-        default: kern = sweep_quad_kernel<NV, true, true>; break;
+        case 0: kern = g8 ? sweep_quad_kernel<NV, MODE, false, false, 4> : sweep_quad_kernel<NV, MODE, false, false>; break;
+        case 1: kern = g8 ? sweep_quad_kernel<NV, MODE, false, true, 4> : sweep_quad_kernel<NV, MODE, false, true>; break;
+        case 2: kern = sweep_quad_kernel<NV, MODE, true, false>; break;
+        default: kern = sweep_quad_kernel<NV, MODE, true, true>; break;
     }
-    static size_t configured[4] = {0, 0, 0, 0};
+    static size_t configured_all[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    size_t* configured = configured_all[g8 ? 1 : 0];
     if (configured[which] < smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(D3D_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
@@ -338,6 +399,21 @@ int launch_sweep_quad(const SweepParams& p, dim3 grid, cudaStream_t stream, bool
     kern<<<grid, 256, smem, stream>>>(p);
     count_launch();
     return check_launch("sweep_quad_kernel");
+}
+
+// returns -1 when the shape is not covered (the caller falls back to sweep_lean / sweep_base)
+template <int MODE>
+int sweep_quad_dispatch(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee) {
+    if (p.C != 32 || p.W > 16000 || p.H > 16000) return -1;   // 16-bit corner fields in the footprint key
+    // rows leave as 16-byte chunks, every CTA owns a whole 32-pixel row segment
+    if ((p.HW & 31) != 0 || ((p.out_sc | p.out_sd) & 3) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return -1;
+    switch (nv) {
+        case 1: return launch_sweep_quad<1, MODE>(p, grid, stream, ieee);
+        case 2: return launch_sweep_quad<2, MODE>(p, grid, stream, ieee);
+        case 3: return launch_sweep_quad<3, MODE>(p, grid, stream, ieee);
+        case 4: return launch_sweep_quad<4, MODE>(p, grid, stream, ieee);
+        default: return -1;
+    }
 }
 
 }  // namespace d3d

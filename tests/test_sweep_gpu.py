@@ -185,6 +185,12 @@ CASES = [  # v, c, d, h, w, perpixel
     (7, 32, 10, 40, 36, False),      # 6 source views -> 4 channels per lane
     (9, 16, 6, 24, 28, True),        # 8 source views (the maximum)
     (3, 64, 6, 20, 24, False),       # 64 channels
+    # 32 channels, <= 4 source views, H*W a multiple of 32: the four-planes-per-pass kernel (sweep_quad.cuh)
+    (5, 32, 24, 64, 48, False),
+    (5, 32, 18, 64, 48, True),       # per-pixel hypotheses, partial last batch
+    (2, 32, 6, 32, 40, False),       # one source view
+    (3, 32, 9, 40, 48, True),        # two source views
+    (4, 32, 8, 48, 40, False),       # three source views
 ]
 
 
@@ -228,7 +234,7 @@ def test_whu_shaped_rig_matches_oracle(smooth, variant):
     assert rel_norm_err(got, want) < VOL_TOL
 
 
-@pytest.mark.parametrize("groups", [1, 4, 8, 32])
+@pytest.mark.parametrize("groups", [1, 4, 8, 16, 32])
 def test_group_corr_matches_oracle(groups):
     _, proj, feats, hyps = _scene(5, 32, 10, 40, 52, seed=4)
     want = sweep_torch.groupwise_correlation_volume(_views(feats), proj, hyps, groups)[0]
@@ -244,9 +250,10 @@ def test_group_corr_wide_groups_lane_reduction():
     assert rel_norm_err(got, want) < VOL_TOL
 
 
+@pytest.mark.parametrize("c,h,w", [(16, 36, 44), (32, 40, 48)])     # base kernel / four-planes-per-pass kernel
 @pytest.mark.parametrize("eps_num", [False, True])
-def test_weighted_product_matches_oracle(eps_num):
-    v, c, d, h, w = 5, 16, 8, 36, 44
+def test_weighted_product_matches_oracle(eps_num, c, h, w):
+    v, d = 5, 8
     _, proj, feats, hyps = _scene(v, c, d, h, w, seed=7, perpixel=True)
     g = torch.Generator().manual_seed(1)
     weights = [torch.rand(1, 1, h // 2, w // 2, generator=g) for _ in range(v - 1)]
