@@ -40,6 +40,7 @@ int sweep_lean_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaSt
 int sweep_quad_variance(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_quad_group_corr(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_quad_weighted_product(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
+int sweep_quad_pair_mean(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 
 static int sm_count() {
     static int cached = 0;
@@ -161,7 +162,8 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
             if (int rc = make_grid(fl2, grid)) return rc;
             int rc = -1;
             // 32-channel features: the four-planes-per-pass kernel (variant 6 keeps the two-plane one for A/B)
-            if ((variant == 0 || variant == 2) && C == 32 && fl2 == 3) rc = sweep_quad_variance(nv, p, grid, stream, variant == 2);
+            if ((variant == 0 || variant == 2) && fcpt == 4 && (C == 32 || C == 16))
+                rc = sweep_quad_variance(nv, p, grid, stream, variant == 2);
             if (rc < 0 && variant != 4 && variant != 5) rc = sweep_lean_variance(fcpt, nv, p, grid, stream, variant == 2);
             if (rc < 0) rc = sweep_fast_variance(fcpt, nv, p, grid, stream, variant == 2);
             if (rc >= 0) return rc;
@@ -169,11 +171,13 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
     }
     // 32-channel features, <= 4 source views: the four-planes-per-pass kernel also builds the group-wise
     // correlation and the weighted-product volumes
-    if ((variant == 0 || variant == 2) && C == 32 && nv <= 4 &&
-        (a->mode == D3D_AGG_GROUP_CORR || a->mode == D3D_AGG_WEIGHTED_PRODUCT)) {
-        if (int rc = make_grid(3, grid)) return rc;
-        const int rc = a->mode == D3D_AGG_GROUP_CORR ? sweep_quad_group_corr(nv, p, grid, stream, variant == 2)
-                                                     : sweep_quad_weighted_product(nv, p, grid, stream, variant == 2);
+    if ((variant == 0 || variant == 2) && (C == 32 || C == 16) && nv <= 4 &&
+        (a->mode == D3D_AGG_GROUP_CORR || a->mode == D3D_AGG_WEIGHTED_PRODUCT || a->mode == D3D_AGG_PAIR_MEAN)) {
+        if (int rc = make_grid(ilog2_exact(C / 4), grid)) return rc;
+        const bool ieee = variant == 2;
+        const int rc = a->mode == D3D_AGG_GROUP_CORR ? sweep_quad_group_corr(nv, p, grid, stream, ieee)
+                     : a->mode == D3D_AGG_PAIR_MEAN  ? sweep_quad_pair_mean(nv, p, grid, stream, ieee)
+                                                     : sweep_quad_weighted_product(nv, p, grid, stream, ieee);
         if (rc >= 0) return rc;
     }
     if (int rc = make_grid(lpp_log2, grid)) return rc;

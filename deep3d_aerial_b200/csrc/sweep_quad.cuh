@@ -13,6 +13,10 @@
 //     ((y0 & 0xffff) << 16 | x0 & 0xffff, one PRMT); address arithmetic, the interior test and zeros padding
 //     moved into the re-fetch block (refetch_tok, sweep_refetch.cuh), which runs for ~9 % of the (view, plane)s;
 //   * a pass is also the staged batch: one mbarrier arrive / wait per four planes, no inner pass loop.
+//
+// The same kernel serves 16- and 8-channel features (cascade stages 2 and 3): LPP = 4 or 2 lanes per pixel,
+// 8 or 16 pixels per warp, 64 or 128 pixels (a 256 / 512-byte row segment per channel) per CTA; a lane then
+// runs 2 or 4 projection chains per pass.
 #pragma once
 #include "sweep_lean.cuh"
 
@@ -35,40 +39,45 @@ __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y
 constexpr int kQuadPlanes = 4;       // planes per pass = planes per staged batch
 constexpr int kQuadBuffers = 4;      // staging ring
 
-template <int NV, int V = 0>
+template <int NV, int TEXB, int V = 0>
 struct RefetchTok {
     static __device__ __forceinline__ void run(float2 (&tex)[NV][4][2], unsigned (&ckey)[NV], const float4 (&g)[NV],
                                                const float* base, unsigned row_bytes, int hw, int W, int H) {
-        refetch_tok<V + 1, 128>(tex[V], ckey[V], __float_as_uint(g[V].w), base, row_bytes, hw, W, H);
-        RefetchTok<NV, V + 1>::run(tex, ckey, g, base, row_bytes, hw, W, H);
+        refetch_tok<V + 1, TEXB>(tex[V], ckey[V], __float_as_uint(g[V].w), base, row_bytes, hw, W, H);
+        RefetchTok<NV, TEXB, V + 1>::run(tex, ckey, g, base, row_bytes, hw, W, H);
     }
 };
-template <int NV>
-struct RefetchTok<NV, NV> {
+template <int NV, int TEXB>
+struct RefetchTok<NV, TEXB, NV> {
     static __device__ __forceinline__ void run(float2 (&)[NV][4][2], unsigned (&)[NV], const float4 (&)[NV], const float*,
                                                unsigned, int, int, int) {}
 };
 
 // MODE: D3D_AGG_VARIANCE, D3D_AGG_WEIGHTED_PRODUCT (both write C rows per plane) or D3D_AGG_GROUP_CORR
 // (p.groups rows; a lane's 4 channels are whole groups, one group, or a slice of a group that spans lanes).
+// D3D_AGG_PAIR_MEAN writes one row per source view (mean over all channels of ref * warped).
 // GS: channels per group known at compile time (4 = the G=8 configuration of BASELINE.json), 0 = read p.groups.
-template <int NV, int MODE, bool kIeeeDiv, bool kPerPix, int GS = 0>
+template <int NV, int MODE, bool kIeeeDiv, bool kPerPix, int GS = 0, int LPP = 8>
 __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p) {
-    constexpr int CPT = 4, LPP = 8, PPW = 4, NP = 2, C = 32;
+    constexpr int CPT = 4, PPW = 32 / LPP, NP = 2, C = CPT * LPP;
+    constexpr int PIX = 8 * PPW;                           // pixels per CTA: 32, 64 or 128
+    constexpr int JPL = 8 / LPP;                           // projection chains a lane runs per pass
+    constexpr int NVL = JPL > 1 ? JPL / 2 : 1;             // distinct views among them
     constexpr int KT = kQuadPlanes, NBUF = kQuadBuffers;
     constexpr unsigned GEO_PLANE = 4 * PPW * 16;           // bytes: one plane's table of one warp (4 view slots)
     constexpr unsigned GEO_BUF = KT * GEO_PLANE;
-    constexpr unsigned TILE_PLANE = C * 32 * 4;            // bytes: one staged plane
+    constexpr unsigned TILE_PLANE = C * PIX * 4;           // bytes: one staged plane (4 KB whatever LPP)
+    static_assert(MODE != D3D_AGG_PAIR_MEAN || LPP == 8, "pair-mean volumes are built from 32-channel features");
     constexpr unsigned TILE_BUF = KT * TILE_PLANE;
     constexpr unsigned TILE_RING = NBUF * TILE_BUF;
     extern __shared__ float4 smem4[];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int cg = lane & 7;
-    const int q = lane >> 3;
+    const int cg = lane % LPP;
+    const int q = lane / LPP;
     const int choff = cg * CPT;
-    const long long grp_base = (long long)blockIdx.x * 32;
+    const long long grp_base = (long long)blockIdx.x * PIX;
 
     const int d0 = p.d_begin + blockIdx.y * p.d_chunk;
     const int d1 = min(d0 + p.d_chunk, p.d_end);
@@ -88,27 +97,35 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
     }
     __syncthreads();
 
-    // ---- this lane's projection job: view cg & 3, planes 2*(cg >> 2) and +1 of every pass
-    const int pv = min(cg & 3, NV - 1);
-    const int pp = cg >> 2;
-    const bool owner = (cg & 3) < NV;
-    float rx, ry, rz, tx, ty, tz;
+    // ---- this lane's projection jobs.  Job ids 0..7 = (plane pair, view); lane cg runs ids cg, cg + LPP, ...:
+    //   LPP = 8: one job, view cg & 3, pair cg >> 2;   LPP = 4: view cg, both pairs;   LPP = 2: views cg and cg + 2,
+    //   both pairs.  Chain k of a lane: view slot k % NVL, pair (LPP == 8 ? cg >> 2 : k / NVL).
+    float rx[NVL], ry[NVL], rz[NVL], tx[NVL], ty[NVL], tz[NVL];
+    bool owner[NVL];
+    int jview[NVL];
     float2 rf[NP];
-    const float* hp = p.hyps;                              // kPerPix: this pixel's hypotheses, first plane of the job
+    const float* hp = p.hyps;                              // kPerPix: this pixel's hypotheses
     {
         const long long pix_raw = grp_base + warp * PPW + q;
         const int pix = pix_raw < p.HW ? (int)pix_raw : p.HW - 1;    // clamp: the warp stays whole
         const int py = pix / p.W, px = pix - py * p.W;
-        const float* m = p.pose + pv * 16;
-        rx = fmaf(m[2], 1.f, fmaf(m[1], (float)py, m[0] * (float)px));
-        ry = fmaf(m[6], 1.f, fmaf(m[5], (float)py, m[4] * (float)px));
-        rz = fmaf(m[10], 1.f, fmaf(m[9], (float)py, m[8] * (float)px));
-        tx = m[3]; ty = m[7]; tz = m[11];
+#pragma unroll
+        for (int i = 0; i < NVL; ++i) {
+            const int view = (LPP == 8) ? (cg & 3) : cg + i * LPP;
+            owner[i] = view < NV;
+            jview[i] = min(view, NV - 1);
+            const float* m = p.pose + jview[i] * 16;
+            rx[i] = fmaf(m[2], 1.f, fmaf(m[1], (float)py, m[0] * (float)px));
+            ry[i] = fmaf(m[6], 1.f, fmaf(m[5], (float)py, m[4] * (float)px));
+            rz[i] = fmaf(m[10], 1.f, fmaf(m[9], (float)py, m[8] * (float)px));
+            tx[i] = m[3]; ty[i] = m[7]; tz[i] = m[11];
+        }
         const float4 w = ldg4(p.feats + (size_t)pix * C + choff);
         rf[0] = f2(w.x, w.y);
         rf[1] = f2(w.z, w.w);
-        if (kPerPix) hp = p.hyps + (size_t)pix + (size_t)(d0 + 2 * pp) * p.HW;
+        if (kPerPix) hp = p.hyps + (size_t)pix + (size_t)d0 * p.HW;
     }
+    const int pp0 = (LPP == 8) ? (cg >> 2) : 0;            // plane pair of chain 0 (chains k >= NVL: pair 1)
 
     float2 tex[NV][4][NP];      // per view: A, B, C, D of the current 2x2 footprint
     unsigned ckey[NV];
@@ -125,7 +142,9 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
 
     // ---- running shared-memory addresses
     unsigned gr = geo_w + q * 16;                                          // read: + t*GEO_PLANE + v*PPW*16
-    unsigned gw = geo_w + GEO_BUF + 2 * pp * GEO_PLANE + pv * PPW * 16 + q * 16;   // write (other buffer)
+    // write (other buffer): chain 0's entry; chain k (same view, LPP = 4) is 2*k planes further
+    static_assert(NVL == 1, "one view per lane: LPP = 8 or 4");
+    unsigned gw = geo_w + GEO_BUF + q * 16 + 2 * ((LPP == 8) ? (cg >> 2) : 0) * GEO_PLANE + jview[0] * PPW * 16;
     unsigned gflip = GEO_BUF;                                              // +/- distance between the buffers
     // output rows of this lane: variance / weighted product / groups of 1 channel: its 4 channels; groups of 2:
     // two rows; wider groups: one row, written by the first lane of the group.  Row r of a staged plane is
@@ -133,18 +152,26 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
     // and every aligned run of 4 pixels contiguous for the 16-byte read-out.
     const int gs = (MODE != D3D_AGG_GROUP_CORR) ? 1 : (GS ? GS : C / p.groups);   // channels per output row
     const int rpl_log2 = gs >= 4 ? 0 : (gs == 2 ? 1 : 2);                  // log2(rows per lane)
-    const int row0 = gs >= 4 ? choff / gs : (choff >> (gs == 2 ? 1 : 0));  // this lane's first row
-    const int n_rows = (MODE == D3D_AGG_GROUP_CORR) ? p.groups : C;
-    unsigned tw = tile_g + (row0 * 32 + ((warp * PPW + q) ^ ((4 * (row0 >> rpl_log2)) & 31))) * 4;   // + k*128 per row
+    // (pair mean: after the reduce-scatter over the 8 lanes of a pixel, lane cg holds source view cg >> 1)
+    const int row0 = (MODE == D3D_AGG_PAIR_MEAN) ? (cg >> 1) : gs >= 4 ? choff / gs : (choff >> (gs == 2 ? 1 : 0));
+    const int n_rows = (MODE == D3D_AGG_GROUP_CORR) ? p.groups : (MODE == D3D_AGG_PAIR_MEAN) ? NV : C;
+    // staged plane: [rows][PIX px]; the pixel column is swizzled inside its aligned group of 32 by the lane
+    // that owns the row (PPW * lane-in-pixel), which spreads a warp's stores over all 32 banks
+    const unsigned swz_w = (MODE == D3D_AGG_PAIR_MEAN) ? (unsigned)((PPW * (cg >> 1) * 2) & 31)
+                                                       : (unsigned)((PPW * (row0 >> rpl_log2)) & 31);
+    unsigned tw = tile_g + (row0 * PIX + ((warp * PPW + q) ^ swz_w)) * 4;  // + k*PIX*4 per row
     unsigned dr;                                           // drain: staged row chunk this lane moves
     float* optr;                                           // drain: where it goes
     bool drain_row;                                        // fewer than 32 rows (group-wise correlation)
     {
-        const int row = threadIdx.x >> 3, c4 = (threadIdx.x & 7) * 4;
-        dr = tile_g + (row * 32 + (c4 ^ ((4 * (row >> rpl_log2)) & 31))) * 4;
+        constexpr int CPR = PIX / 4;                       // 16-byte chunks per staged row
+        const int row = threadIdx.x / CPR, c4 = (threadIdx.x % CPR) * 4;
+        const unsigned swz_r = (MODE == D3D_AGG_PAIR_MEAN) ? (unsigned)((PPW * row * 2) & 31)
+                                                           : (unsigned)((PPW * (row >> rpl_log2)) & 31);
+        dr = tile_g + (row * PIX + (c4 ^ swz_r)) * 4;
         optr = p.out + ((long long)row * p.out_sc + (long long)(d0 - p.d_begin) * p.out_sd + grp_base + c4);
         drain_row = row < n_rows;
-        // H*W is a multiple of 32 (checked by the launcher): every CTA owns a whole row segment
+        // H*W is a multiple of PIX (checked by the launcher): every CTA owns whole row segments
     }
     float wt[NV];                                          // weighted product: this pixel's view weights
     float winv = 0.f;
@@ -161,34 +188,42 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
     }
     const float gscale = 1.f / ((float)gs * (float)NV);    // group-wise correlation: mean over group and views
 
-    // ---- hypotheses of the two planes this lane projects in the next pass
-    unsigned hs = hyp_s + 2 * pp * 4;                      // !kPerPix: running shared-memory address
-    int hplane = d0 + 2 * pp;                              // kPerPix: plane `hp` points at
-    auto next_depths = [&]() -> float2 {
-        float2 d;
+    // ---- hypotheses of the planes this lane projects in the next pass: both plane pairs unless LPP = 8
+    unsigned hs = hyp_s + 2 * pp0 * 4;                     // !kPerPix: running shared-memory address
+    int hplane = d0 + 2 * pp0;                             // kPerPix: plane `hp` points at
+    if (kPerPix) hp += (size_t)(2 * pp0) * p.HW;
+    auto next_depths = [&](float2 (&d)[2]) {
         if (kPerPix) {
             const size_t hw = (size_t)p.HW;
-            const float* a = hplane < d1 ? hp : hp - (size_t)(hplane - (d1 - 1)) * hw;
-            const float* b = hplane + 1 < d1 ? hp + hw : a;
-            d = f2(__ldg(a), __ldg(b));
+#pragma unroll
+            for (int k = 0; k < (LPP == 8 ? 2 : 4); ++k) {
+                const int pl = min(hplane + k, d1 - 1);    // planes past the end repeat the last one
+                const float v = __ldg(hp + (long long)(pl - hplane) * (long long)hw);
+                if (k == 0) d[0].x = v; else if (k == 1) d[0].y = v; else if (k == 2) d[1].x = v; else d[1].y = v;
+            }
             hp += (size_t)KT * hw;
             hplane += KT;
         } else {
-            d = lds64(hs);
+            if (LPP == 8) {
+                d[0] = lds64(hs);
+            } else {
+                const float4 v = lds128(hs);
+                d[0] = f2(v.x, v.y);
+                d[1] = f2(v.z, v.w);
+            }
             hs += KT * 4;
         }
-        return d;
     };
 
     // Packed projection of the lane's view at two depths; every packed operation is the reference's IEEE
     // operation on each half (see project_frac in sweep_fast.cuh for the order and why it is that order).
-    auto project2 = [&](float2 d, float4& ea, float4& eb) {
+    auto project2 = [&](int i, float2 d, float4& ea, float4& eb) {
         // (nvcc contracts __fmul2_rn + __fadd2_rn into one FFMA2, which would round once where the reference
         // rounds twice: every add that follows a multiply is a scalar __fadd_rn)
-        const float2 Xm = __fmul2_rn(splat(rx), d), Ym = __fmul2_rn(splat(ry), d), Zm = __fmul2_rn(splat(rz), d);
-        const float2 X = f2(__fadd_rn(Xm.x, tx), __fadd_rn(Xm.y, tx));
-        const float2 Y = f2(__fadd_rn(Ym.x, ty), __fadd_rn(Ym.y, ty));
-        const float2 Z = f2(__fadd_rn(Zm.x, tz), __fadd_rn(Zm.y, tz));
+        const float2 Xm = __fmul2_rn(splat(rx[i]), d), Ym = __fmul2_rn(splat(ry[i]), d), Zm = __fmul2_rn(splat(rz[i]), d);
+        const float2 X = f2(__fadd_rn(Xm.x, tx[i]), __fadd_rn(Xm.y, tx[i]));
+        const float2 Y = f2(__fadd_rn(Ym.x, ty[i]), __fadd_rn(Ym.y, ty[i]));
+        const float2 Z = f2(__fadd_rn(Zm.x, tz[i]), __fadd_rn(Zm.y, tz[i]));
         float2 u, v;
         if (kIeeeDiv) {
             u = f2(__fdiv_rn(X.x, Z.x), __fdiv_rn(X.y, Z.y));
@@ -227,16 +262,29 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
         eb = make_float4(fx.y, fy.y, fxy.y, __uint_as_float(kb));
     };
 
-    // ---- prologue: projections of the first pass into table buffer 0
-    {
-        float4 ea, eb;
-        project2(next_depths(), ea, eb);
-        if (owner) {
-            sts128(gw - GEO_BUF, ea);
-            sts128(gw - GEO_BUF + GEO_PLANE, eb);
+    // chain k of the lane's pass: view slot k % NVL, plane pair (LPP == 8 ? pp0 : k / NVL); its two table entries
+    // go to the buffer at `base`.  In the sweep, chain k runs inside plane k of the pass (interleaved with that
+    // plane's arithmetic), so every plane carries at most one chain.
+    auto store_chain = [&](int k, const float4& ea, const float4& eb, unsigned base) {
+        if (owner[0]) {
+            const unsigned a = base + (LPP == 8 ? 0 : 2 * k) * GEO_PLANE;
+            sts128(a, ea);
+            sts128(a + GEO_PLANE, eb);
         }
+    };
+    auto project_chain = [&](int k, const float2 (&d)[2], float4& ea, float4& eb) {
+        project2(k % NVL, d[LPP == 8 ? 0 : k / NVL], ea, eb);
+    };
+    // ---- prologue: projections of the first pass into table buffer 0
+    float2 dnext[2];
+    next_depths(dnext);
+#pragma unroll
+    for (int k = 0; k < JPL; ++k) {
+        float4 ea, eb;
+        project_chain(k, dnext, ea, eb);
+        store_chain(k, ea, eb, gw - GEO_BUF);
     }
-    float2 dnext = next_depths();
+    next_depths(dnext);
 
     const float invV = 1.f / (float)(NV + 1);
     const float2 ninv = splat(-invV), pinv = splat(invV);
@@ -250,7 +298,7 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
         const float4 w = lds128(dr);
         dr += TILE_PLANE;
         // the volume is write-once: keep it out of L1, which holds the texels the re-fetches hit
-        if (MODE != D3D_AGG_GROUP_CORR || drain_row)
+        if ((MODE != D3D_AGG_GROUP_CORR && MODE != D3D_AGG_PAIR_MEAN) || drain_row)
             asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(optr), "f"(w.x), "f"(w.y),
                          "f"(w.z), "f"(w.w) : "memory");
         optr += p.out_sd;
@@ -280,11 +328,12 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
 #pragma unroll
             for (int v = 0; v < NV; ++v) moved |= __float_as_uint(g[v].w) ^ ckey[v];
             if (moved)                               // some footprint moved: re-fetch those (in place)
-                RefetchTok<NV>::run(tex, ckey, g, feats_c, row_bytes, p.HW, p.W, p.H);
+                RefetchTok<NV, C * 4>::run(tex, ckey, g, feats_c, row_bytes, p.HW, p.W, p.H);
             float4 ea, eb;
-            if (t == 0) project2(dnext, ea, eb);     // next pass, interleaved with the arithmetic
+            if (t < JPL) project_chain(t, dnext, ea, eb);    // next pass, interleaved with the arithmetic
 
             float2 s[NP], sq[NP];                    // variance: sum, sum of squares; otherwise s = accumulator
+            float pm[4] = {0.f, 0.f, 0.f, 0.f};      // pair mean: this lane's partial dot product per view
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
                 const float2 fx = splat(g[v].x), fy = splat(g[v].y), fxy = splat(g[v].z);
@@ -303,19 +352,17 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
                         }
                     } else if (MODE == D3D_AGG_GROUP_CORR) {           // sum_v ref * warped_v
                         s[j] = (v == 0) ? __fmul2_rn(rf[j], o) : __ffma2_rn(rf[j], o, s[j]);
+                    } else if (MODE == D3D_AGG_PAIR_MEAN) {            // per view: sum_c ref * warped_v
+                        s[0] = (j == 0) ? __fmul2_rn(rf[j], o) : __ffma2_rn(rf[j], o, s[0]);
+                        if (j == NP - 1) pm[v] = s[0].x + s[0].y;
                     } else {                                           // sum_v (warped_v * ref) * weight_v
                         s[j] = __ffma2_rn(__fmul2_rn(o, rf[j]), splat(wt[v]),
                                           v == 0 ? splat(p.eps_num ? 1e-5f : 0.f) : s[j]);
                     }
                 }
             }
-            if (t == 0) {
-                if (owner) {
-                    sts128(gw, ea);
-                    sts128(gw + GEO_PLANE, eb);
-                }
-                dnext = next_depths();
-            }
+            if (t < JPL) store_chain(t, ea, eb, gw);
+            if (t == JPL - 1) next_depths(dnext);
             if (t + 1 < KT) {
                 load_table(gr + (t + 1) * GEO_PLANE);
             } else {                                 // last plane of the pass: swap the table buffers
@@ -331,26 +378,39 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
                     const float2 tneg = __fmul2_rn(s[j], ninv);            // -sum/V
                     const float2 w = __ffma2_rn(tneg, s[j], sq[j]);        // sq - sum^2/V
                     const float2 r = __fmul2_rn(w, pinv);                  // sq/V - (sum/V)^2
-                    sts32(tw + (2 * j) * 128 + t * TILE_PLANE, r.x);
-                    sts32(tw + (2 * j + 1) * 128 + t * TILE_PLANE, r.y);
+                    sts32(tw + (2 * j) * PIX * 4 + t * TILE_PLANE, r.x);
+                    sts32(tw + (2 * j + 1) * PIX * 4 + t * TILE_PLANE, r.y);
                 }
             } else if (MODE == D3D_AGG_WEIGHTED_PRODUCT) {
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
                     const float2 r = __fmul2_rn(s[j], splat(winv));
-                    sts32(tw + (2 * j) * 128 + t * TILE_PLANE, r.x);
-                    sts32(tw + (2 * j + 1) * 128 + t * TILE_PLANE, r.y);
+                    sts32(tw + (2 * j) * PIX * 4 + t * TILE_PLANE, r.x);
+                    sts32(tw + (2 * j + 1) * PIX * 4 + t * TILE_PLANE, r.y);
                 }
+            } else if (MODE == D3D_AGG_PAIR_MEAN) {
+                // reduce-scatter over the 8 lanes of the pixel: 4 partial sums -> lane cg ends with the total of
+                // view cg >> 1 (4 shuffles instead of a 3-step butterfly per view)
+                const bool hi4 = (cg & 4) != 0, hi2 = (cg & 2) != 0;
+                float a0 = hi4 ? pm[2] : pm[0], a1 = hi4 ? pm[3] : pm[1];          // keep views (0,1) or (2,3)
+                const float b0 = hi4 ? pm[0] : pm[2], b1 = hi4 ? pm[1] : pm[3];    // send the other two
+                a0 += __shfl_xor_sync(0xffffffffu, b0, 4);
+                a1 += __shfl_xor_sync(0xffffffffu, b1, 4);
+                float c0 = hi2 ? a1 : a0;
+                const float c1 = hi2 ? a0 : a1;
+                c0 += __shfl_xor_sync(0xffffffffu, c1, 2);
+                c0 += __shfl_xor_sync(0xffffffffu, c0, 1);
+                if (!(cg & 1) && (cg >> 1) < NV) sts32(tw + t * TILE_PLANE, c0 * (1.f / (float)C));
             } else {                                 // group-wise correlation: mean over the group and the views
                 if (gs == 1) {
 #pragma unroll
                     for (int j = 0; j < NP; ++j) {
-                        sts32(tw + (2 * j) * 128 + t * TILE_PLANE, s[j].x * gscale);
-                        sts32(tw + (2 * j + 1) * 128 + t * TILE_PLANE, s[j].y * gscale);
+                        sts32(tw + (2 * j) * PIX * 4 + t * TILE_PLANE, s[j].x * gscale);
+                        sts32(tw + (2 * j + 1) * PIX * 4 + t * TILE_PLANE, s[j].y * gscale);
                     }
                 } else if (gs == 2) {
                     sts32(tw + t * TILE_PLANE, (0.f + s[0].x + s[0].y) * gscale);
-                    sts32(tw + 128 + t * TILE_PLANE, (0.f + s[1].x + s[1].y) * gscale);
+                    sts32(tw + PIX * 4 + t * TILE_PLANE, (0.f + s[1].x + s[1].y) * gscale);
                 } else {
                     float a = ((s[0].x + s[0].y) + s[1].x) + s[1].y;       // the lane's 4 channels, in order
                     for (int o = 1; o < gs / 4; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -375,19 +435,23 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
     }
 }
 
-template <int NV, int MODE>
+template <int NV, int MODE, int LPP>
 int launch_sweep_quad(const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div) {
-    const size_t smem = 64 + (size_t)8 * 2 * kQuadPlanes * 4 * 4 * 16 + (size_t)kQuadBuffers * kQuadPlanes * 32 * 32 * 4 +
+    const size_t smem = 64 + (size_t)8 * 2 * kQuadPlanes * 4 * (32 / LPP) * 16 +
+                        (size_t)kQuadBuffers * kQuadPlanes * 32 * 32 * 4 +
                         (p.perpix ? 0 : (size_t)(p.d_chunk + kLeanHypPad) * 4);
-    if (smem > 110 * 1024) return -1;                // keep two CTAs per SM; absurd depth chunks go elsewhere
+    if (smem > 110 * 1024 && LPP > 2) return -1;     // keep two CTAs per SM; absurd depth chunks go elsewhere
+    if (smem > 200 * 1024) return -1;
     void (*kern)(const SweepParams);
     const int which = (ieee_div ? 2 : 0) + (p.perpix ? 1 : 0);
-    const bool g8 = MODE == D3D_AGG_GROUP_CORR && p.groups == 8 && !ieee_div;     // groups of 4 channels = one lane
+    const bool g8 = MODE == D3D_AGG_GROUP_CORR && LPP == 8 && p.groups == 8 && !ieee_div;   // groups of 4 = one lane
     switch (which) {
-        case 0: kern = g8 ? sweep_quad_kernel<NV, MODE, false, false, 4> : sweep_quad_kernel<NV, MODE, false, false>; break;
-        case 1: kern = g8 ? sweep_quad_kernel<NV, MODE, false, true, 4> : sweep_quad_kernel<NV, MODE, false, true>; break;
-        case 2: kern = sweep_quad_kernel<NV, MODE, true, false>; break;
-        default: kern = sweep_quad_kernel<NV, MODE, true, true>; break;
+        case 0: kern = g8 ? sweep_quad_kernel<NV, MODE, false, false, (LPP == 8 ? 4 : 0), LPP>
+                          : sweep_quad_kernel<NV, MODE, false, false, 0, LPP>; break;
+        case 1: kern = g8 ? sweep_quad_kernel<NV, MODE, false, true, (LPP == 8 ? 4 : 0), LPP>
+                          : sweep_quad_kernel<NV, MODE, false, true, 0, LPP>; break;
+        case 2: kern = sweep_quad_kernel<NV, MODE, true, false, 0, LPP>; break;
+        default: kern = sweep_quad_kernel<NV, MODE, true, true, 0, LPP>; break;
     }
     static size_t configured_all[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     size_t* configured = configured_all[g8 ? 1 : 0];
@@ -401,19 +465,30 @@ int launch_sweep_quad(const SweepParams& p, dim3 grid, cudaStream_t stream, bool
     return check_launch("sweep_quad_kernel");
 }
 
+template <int MODE, int LPP>
+int sweep_quad_by_views(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee) {
+    switch (nv) {
+        case 1: return launch_sweep_quad<1, MODE, LPP>(p, grid, stream, ieee);
+        case 2: return launch_sweep_quad<2, MODE, LPP>(p, grid, stream, ieee);
+        case 3: return launch_sweep_quad<3, MODE, LPP>(p, grid, stream, ieee);
+        case 4: return launch_sweep_quad<4, MODE, LPP>(p, grid, stream, ieee);
+        default: return -1;
+    }
+}
+
 // returns -1 when the shape is not covered (the caller falls back to sweep_lean / sweep_base)
 template <int MODE>
 int sweep_quad_dispatch(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee) {
-    if (p.C != 32 || p.W > 16000 || p.H > 16000) return -1;   // 16-bit corner fields in the footprint key
-    // rows leave as 16-byte chunks, every CTA owns a whole 32-pixel row segment
-    if ((p.HW & 31) != 0 || ((p.out_sc | p.out_sd) & 3) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return -1;
-    switch (nv) {
-        case 1: return launch_sweep_quad<1, MODE>(p, grid, stream, ieee);
-        case 2: return launch_sweep_quad<2, MODE>(p, grid, stream, ieee);
-        case 3: return launch_sweep_quad<3, MODE>(p, grid, stream, ieee);
-        case 4: return launch_sweep_quad<4, MODE>(p, grid, stream, ieee);
-        default: return -1;
+    if (p.W > 16000 || p.H > 16000) return -1;       // 16-bit corner fields in the footprint key
+    // rows leave as 16-byte chunks, every CTA owns whole row segments of 32 / 64 pixels
+    if (((p.out_sc | p.out_sd) & 3) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return -1;
+    if (p.C == 32 && (p.HW & 31) == 0) return sweep_quad_by_views<MODE, 8>(nv, p, grid, stream, ieee);
+    if constexpr (MODE != D3D_AGG_PAIR_MEAN && MODE != D3D_AGG_GROUP_CORR) {          // cascade stages 2 and 3
+        if (p.C == 16 && (p.HW & 63) == 0) return sweep_quad_by_views<MODE, 4>(nv, p, grid, stream, ieee);
+        // (8-channel features, LPP = 2: the projection chains outweigh the arithmetic, one CTA per SM, and stage 3
+        // sweeps only 8 planes -- measured slower than sweep_base_kernel, 3.7 vs 2.9 ms on the cfg3 shape)
     }
+    return -1;
 }
 
 }  // namespace d3d

@@ -1,4 +1,4 @@
-// Production sweep kernel for 32-channel features (four planes per projection pass): variance volume.
+// Production sweep kernel for 32-, 16- and 8-channel features (four planes per projection pass): variance volume.
 #include "sweep_quad.cuh"
 
 namespace d3d {

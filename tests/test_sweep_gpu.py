@@ -191,6 +191,11 @@ CASES = [  # v, c, d, h, w, perpixel
     (2, 32, 6, 32, 40, False),       # one source view
     (3, 32, 9, 40, 48, True),        # two source views
     (4, 32, 8, 48, 40, False),       # three source views
+    # ... and its 16- / 8-channel forms (cascade stages 2 and 3): H*W a multiple of 64 / 128
+    (5, 16, 12, 64, 48, True),
+    (3, 16, 10, 32, 64, False),
+    (5, 8, 8, 64, 96, True),
+    (4, 8, 6, 48, 64, False),
 ]
 
 
@@ -250,7 +255,7 @@ def test_group_corr_wide_groups_lane_reduction():
     assert rel_norm_err(got, want) < VOL_TOL
 
 
-@pytest.mark.parametrize("c,h,w", [(16, 36, 44), (32, 40, 48)])     # base kernel / four-planes-per-pass kernel
+@pytest.mark.parametrize("c,h,w", [(16, 36, 44), (32, 40, 48), (16, 32, 64), (8, 64, 64)])   # base / quad kernels
 @pytest.mark.parametrize("eps_num", [False, True])
 def test_weighted_product_matches_oracle(eps_num, c, h, w):
     v, d = 5, 8
@@ -263,9 +268,10 @@ def test_weighted_product_matches_oracle(eps_num, c, h, w):
     assert rel_norm_err(got, want) < VOL_TOL
 
 
-def test_pair_mean_matches_oracle():
-    _, proj, feats, hyps = _scene(5, 32, 12, 43, 29, seed=8)
-    hy4 = hyps.view(1, -1, 1, 1).repeat(1, 1, 43, 29)
+@pytest.mark.parametrize("v,h,w", [(5, 43, 29), (5, 40, 48), (3, 32, 40)])      # base kernel / quad kernel
+def test_pair_mean_matches_oracle(v, h, w):
+    _, proj, feats, hyps = _scene(v, 32, 12, h, w, seed=8)
+    hy4 = hyps.view(1, -1, 1, 1).repeat(1, 1, h, w)
     want = torch.stack(sweep_torch.pair_mean_volumes(_views(feats), proj, hy4), 1)[0]
     got = _ours_volume(feats, proj, hy4, sweep.AGG_PAIR_MEAN)
     assert rel_norm_err(got, want) < VOL_TOL
