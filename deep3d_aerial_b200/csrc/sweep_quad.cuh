@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
     float rx[NVL], ry[NVL], rz[NVL], tx[NVL], ty[NVL], tz[NVL];
     bool owner[NVL];
     int jview[NVL];
-    float2 rf[NP];
+    float2 rf[NP], rf2[NP];
     const float* hp = p.hyps;                              // kPerPix: this pixel's hypotheses
     {
         const long long pix_raw = grp_base + warp * PPW + q;
@@ -123,6 +123,8 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
         const float4 w = ldg4(p.feats + (size_t)pix * C + choff);
         rf[0] = f2(w.x, w.y);
         rf[1] = f2(w.z, w.w);
+        rf2[0] = __fmul2_rn(rf[0], rf[0]);                 // variance: ref^2 once per pixel, not once per plane
+        rf2[1] = __fmul2_rn(rf[1], rf[1]);
         if (kPerPix) hp = p.hyps + (size_t)pix + (size_t)d0 * p.HW;
     }
     const int pp0 = (LPP == 8) ? (cg >> 2) : 0;            // plane pair of chain 0 (chains k >= NVL: pair 1)
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
                     if (MODE == D3D_AGG_VARIANCE) {
                         if (v == 0) {
                             s[j] = __fadd2_rn(rf[j], o);
-                            sq[j] = __ffma2_rn(o, o, __fmul2_rn(rf[j], rf[j]));
+                            sq[j] = __ffma2_rn(o, o, rf2[j]);
                         } else {
                             s[j] = __fadd2_rn(s[j], o);
                             sq[j] = __ffma2_rn(o, o, sq[j]);
@@ -440,8 +442,8 @@ int launch_sweep_quad(const SweepParams& p, dim3 grid, cudaStream_t stream, bool
     const size_t smem = 64 + (size_t)8 * 2 * kQuadPlanes * 4 * (32 / LPP) * 16 +
                         (size_t)kQuadBuffers * kQuadPlanes * 32 * 32 * 4 +
                         (p.perpix ? 0 : (size_t)(p.d_chunk + kLeanHypPad) * 4);
-    if (smem > 110 * 1024 && LPP > 2) return -1;     // keep two CTAs per SM; absurd depth chunks go elsewhere
-    if (smem > 200 * 1024) return -1;
+    if (smem > 110 * 1024) return -1;                // keep two CTAs per SM; absurd depth chunks go elsewhere
+    const size_t smem_req = (p.flags & 8) ? 120 * 1024 : smem;   // DIAGNOSTIC (variant 24): one CTA per SM
     void (*kern)(const SweepParams);
     const int which = (ieee_div ? 2 : 0) + (p.perpix ? 1 : 0);
     const bool g8 = MODE == D3D_AGG_GROUP_CORR && LPP == 8 && p.groups == 8 && !ieee_div;   // groups of 4 = one lane
@@ -455,12 +457,12 @@ int launch_sweep_quad(const SweepParams& p, dim3 grid, cudaStream_t stream, bool
     }
     static size_t configured_all[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     size_t* configured = configured_all[g8 ? 1 : 0];
-    if (configured[which] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(D3D_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
-        configured[which] = smem;
+    if (configured[which] < smem_req) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req);
+        if (e != cudaSuccess) return fail(D3D_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem_req, cudaGetErrorString(e));
+        configured[which] = smem_req;
     }
-    kern<<<grid, 256, smem, stream>>>(p);
+    kern<<<grid, 256, smem_req, stream>>>(p);
     count_launch();
     return check_launch("sweep_quad_kernel");
 }
