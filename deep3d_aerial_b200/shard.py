@@ -38,9 +38,32 @@ def partition(view_ids: Sequence[int], world_size: int, rank: int, mode: str = "
     raise ValueError("unknown partition mode %r" % mode)
 
 
+def bind_host_to_gpu(local_rank: int) -> bool:
+    """Pin this process to the CPUs (and so, by first touch, the memory node) NVML reports as closest to its GPU.
+    With one process per GPU every rank streams its views' features from pinned host memory at the same time
+    (204 MB per view at the WHU-OMVS shape); ranks scheduled on the far socket halve that bandwidth.
+    Best effort: returns False when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        index = local_rank
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                index = int(ids[local_rank])
+        nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(index))
+        return True
+    except Exception:  # noqa: BLE001 -- affinity is an optimisation, never a requirement
+        return False
+
+
 def init(backend: Optional[str] = None) -> tuple:
     """Create the process group when launched under torchrun (WORLD_SIZE > 1); returns world()."""
     rank, size, local = world()
+    if size > 1 and torch.cuda.is_available() and os.environ.get("D3D_NO_AFFINITY") != "1":
+        bind_host_to_gpu(local)
     if size > 1 and not dist.is_initialized():
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
