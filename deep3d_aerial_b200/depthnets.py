@@ -23,6 +23,32 @@ import torch.nn.functional as F
 
 from . import sweep
 
+# Opt-in: record the D-plane "regulariser + streaming soft-argmax" loop of the
+# plane-at-a-time models in a CUDA graph per (module, shape) and replay it per reference view (graphs.py).
+# Off by default: the regulariser must be capture-safe, which holds for the reference's modules but is the
+# caller's promise for anything else.  B = 1 per graph replay keeps the reference's semantics.
+PLANE_LOOP_GRAPHS = False
+
+
+def _plane_loop(owner, tag, step, batch, planes, channels, hw, out_hw, state_shapes, hyps_hw, device):
+    from .graphs import PlaneLoop
+
+    cache = owner.__dict__.setdefault("_d3d_plane_loops", {})
+    key = (tag, batch, planes, channels, tuple(hw), tuple(out_hw), tuple(hyps_hw), str(device))
+    if key not in cache:
+        cache[key] = PlaneLoop(step, batch, planes, channels, hw, out_hw, state_shapes, device, hyps_hw=hyps_hw)
+    return cache[key]
+
+
+def _volume_into(out, features, proj_matrices, depth_values, mode, **kw):
+    """Plane-major cost volume of every batch item written straight into `out` [B,D,C,h,w]."""
+    with torch.no_grad():
+        for b in range(features[0].shape[0]):
+            texels, pose = _scene(features, proj_matrices, b)
+            w = kw.get("weights")
+            sweep.cost_volume(texels, pose, depth_values[b].contiguous(), mode, plane_major=True, out=out[b],
+                              **{**kw, "weights": None if w is None else w[b]})
+
 
 def _check(features, proj_matrices, depth_values, num_depth):
     assert len(features) == len(proj_matrices), "Different number of images and projection matrices"
@@ -151,6 +177,17 @@ def ada_infer_forward(self, features, proj_matrices, depth_values, num_depth, co
     resized = [F.interpolate(confidence_map[i], [img_h, img_w], mode='bilinear', align_corners=False)
                for i in range(n_src)]
     weights = torch.cat(resized, 1)                                                             # [B,V-1,h,w]
+    if PLANE_LOOP_GRAPHS and depth_values.dim() == 4:
+        loop = _plane_loop(self, "ada", self.reg_fuse, b_num, num_depth, ref.shape[1], (img_h, img_w),
+                           (img_h * up, img_w * up), [tuple(state1.shape), tuple(state2.shape)],
+                           tuple(depth_values.shape[2:]), dev)
+        _volume_into(loop.volume, features, proj_matrices, depth_values, sweep.AGG_WEIGHTED_PRODUCT, weights=weights)
+        loop.hyps.copy_(depth_values)
+        depth, conf = loop.replay()
+        for d in range(num_depth):
+            pair_confidence.extend(resized)                                                      # :503, the list quirk
+        return {"depth": depth.clone(), "photometric_confidence": conf.clone(),
+                "pair_confidence": pair_confidence, "pair_result": pair_results}
     similarity = _volume(features, proj_matrices, depth_values, sweep.AGG_WEIGHTED_PRODUCT, plane_major=True,
                          weights=weights)                                                        # [B,D,C,h,w]
     for d in range(num_depth):

@@ -126,6 +126,54 @@ def test_adamvs_infer_matches_golden():
     assert len(out2["pair_confidence"]) == g["n_pair_confidence2"]
 
 
+class _GruLike(torch.nn.Module):
+    """A recurrent stand-in with real state (the golden stand-ins are stateless): enough launches per plane
+    for a CUDA graph to matter, and a result that depends on the order of the planes."""
+
+    def __init__(self, up):
+        super().__init__()
+        self.up = up
+
+    def forward(self, x, s1, s2):
+        s1 = torch.tanh(0.7 * s1 + 0.3 * x[:, :8])
+        s2 = 0.5 * s2 + 0.5 * torch.nn.functional.avg_pool2d(torch.cat([s1, x[:, 8:16]], 1), 2)
+        logit = 1.5 * s1.mean(1, keepdim=True) + torch.nn.functional.interpolate(s2.mean(1, keepdim=True), scale_factor=2)
+        if self.up:
+            logit = torch.nn.functional.interpolate(logit, scale_factor=2, mode="nearest")
+        return logit, s1, s2
+
+
+@pytest.mark.parametrize("in_up", [True, False])
+def test_plane_loop_graph_matches_eager(in_up):
+    """Row f1: the D-plane regulariser + streaming soft-argmax loop replayed from a CUDA graph gives bit for bit
+    what the eager loop gives, on fresh inputs, twice (static buffers are refilled, states re-zeroed)."""
+    v, c, d, h, w = 5, 16, 12, 32, 64
+
+    class Net:
+        pass
+
+    net = Net()
+    net.in_up, net.reg, net.reg_fuse = in_up, standins.reg2d_pair, _GruLike(in_up)
+    outs = {}
+    for graphs in (False, True):
+        depthnets.PLANE_LOOP_GRAPHS = graphs
+        try:
+            for seed in (21, 22):
+                _, proj, feats, hyps = _scene(v, c, d, h, w, seed=seed, perpixel=True)
+                conf = [torch.rand(1, 1, h, w, generator=torch.Generator().manual_seed(seed)).to(DEV) for _ in range(v - 1)]
+                out = depthnets.ada_infer_forward(net, _cuda_views(feats), proj.to(DEV), hyps.to(DEV), d,
+                                                  confidence_map=conf)
+                outs[(graphs, seed)] = (out["depth"].clone(), out["photometric_confidence"].clone(),
+                                        len(out["pair_confidence"]))
+        finally:
+            depthnets.PLANE_LOOP_GRAPHS = False
+    for seed in (21, 22):
+        assert torch.equal(outs[(True, seed)][0], outs[(False, seed)][0])
+        assert torch.equal(outs[(True, seed)][1], outs[(False, seed)][1])
+        assert outs[(True, seed)][2] == outs[(False, seed)][2]
+    assert not torch.equal(outs[(True, 21)][0], outs[(True, 22)][0])
+
+
 def test_adamvs_train_form_matches_golden():
     g = load_golden("ada_train_depthnet")
     w = g["pair_conf"][0, :, 0].to(DEV).contiguous()             # [V-1,h,w]
