@@ -66,6 +66,17 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def measured_traffic(wl):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_traffic.json);
+    None when there is no capture for this workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            rec = json.load(f).get(wl)
+        return None if not rec else int(rec["dram_bytes_read"]) + int(rec["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples the SM clock and the throttle reasons of one GPU WHILE the timed region runs: NVML in-process
     every few milliseconds (the timed region of the default run is ~0.3 s, too short for `nvidia-smi -lms`,
@@ -396,7 +407,7 @@ def run_ours(args):
         "ref_views_per_s": world * 1e3 / ms_step,
         "kernel_ms": {"sweep": k1_ms, "regress": k2_ms},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "fused sweep (warp+aggregate)", "algorithmic_bytes": b1,
+                     "traffic": measured_traffic(wl), "kernel": "fused sweep (warp+aggregate)", "algorithmic_bytes": b1,
                      "peak_source": peak_src, "frac_of_8TBps_nominal": achieved / 8000.0},
         "clocks": clocks,
         "gpu_launches": total_launches,
