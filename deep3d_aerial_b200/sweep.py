@@ -198,6 +198,8 @@ def depth_samples(mode: int, num_depth: int, hw: Tuple[int, int], *, device=None
         device = cur.device
     if device is None:
         raise ValueError("device is required when cur is None")
+    if torch.device(device).type != "cuda":
+        raise RuntimeError("depth_samples asked for %s: the sweep engine only runs on CUDA (no CPU fallback)" % (device,))
     out = torch.empty((num_depth, h, w), device=device, dtype=torch.float32)
     a = _lib.SamplesArgs()
     a.struct_size = C.sizeof(a)
