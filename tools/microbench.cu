@@ -178,6 +178,49 @@ float time_ms(F f, int reps = 3) {
     return best;
 }
 
+// legacy tensor-core path (mma.sync, SASS HMMA): TF32 m16n8k8 and m16n8k4, 8 independent accumulator sets.
+// Asked for DESIGN.md "what comes next": would a 3xTF32 split of the bilinear interpolation (one [planes x
+// corners] x [corners x channels] product per pixel and view) take the interpolation off the FP32 pipe?
+__global__ void k_mma_tf32_k8(float* out) {
+    float c[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+    unsigned a0 = threadIdx.x, a1 = threadIdx.x * 3, a2 = threadIdx.x * 5, a3 = threadIdx.x * 7, b0 = 0x3f800000u, b1 = 0x3f000000u;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void k_mma_tf32_k4(float* out) {
+    float c[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+    unsigned a0 = threadIdx.x, a1 = threadIdx.x * 3, b0 = 0x3f800000u;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m16n8k4.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                         : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                         : "r"(a0), "r"(a1), "r"(b0));
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int main() {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
@@ -207,6 +250,8 @@ int main() {
     rep("FRND.FLOOR (+FFMA)", time_ms([&] { k_floor<<<blocks, threads>>>(out, 1.0001f); }), 8.0 * ITERS);
     rep("rcp IEEE (+FADD)", time_ms([&] { k_rcp<<<blocks, threads>>>(out, 0.5f); }), 8.0 * ITERS);
     rep("rcp.approx (+FADD)", time_ms([&] { k_rcp_approx<<<blocks, threads>>>(out, 0.5f); }), 8.0 * ITERS);
+    rep("mma.sync m16n8k8 tf32", time_ms([&] { k_mma_tf32_k8<<<blocks, threads>>>(out); }), 8.0 * ITERS);
+    rep("mma.sync m16n8k4 tf32", time_ms([&] { k_mma_tf32_k4<<<blocks, threads>>>(out); }), 8.0 * ITERS);
     // store probe: 32 rows x n floats = 12 GB
     long long n = 96LL << 20;
     for (int seg : {4, 8, 16, 32}) {
