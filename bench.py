@@ -311,17 +311,18 @@ def run_ours(args):
     slots = [make_inputs(wl, 1000 * rank + s, dev) for s in range(2)]
     if args.debug_flat_hyps:
         slots = [(f, pr, torch.full_like(hy, float(hy.mean())), lg) for f, pr, hy, lg in slots]
-    poses = [sweep.relative_poses(s[1]) for s in slots]
     texels = torch.empty((v, h, w, c), device=dev)
     volume = torch.empty((cout, d, h, w), device=dev)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
 
     def step(i, events=None):
-        feats, _, hyps, logits = slots[i % 2]
+        feats, proj, hyps, logits = slots[i % 2]
         sweep.to_texels(feats, out=texels)
+        pose = sweep.relative_poses(proj)                       # module.py:528, per source view
+        rays = sweep.reference_rays(pose, h, w)                 # module.py:538 (bit-identical rays at any size)
         if events:
             events[0].record()
-        sweep.cost_volume(texels, poses[i % 2], hyps, agg, groups=groups, out=volume, variant=args.variant)
+        sweep.cost_volume(texels, pose, hyps, agg, groups=groups, out=volume, variant=args.variant, rays=rays)
         if events:
             events[1].record()
             events[2].record()

@@ -30,6 +30,7 @@ class CostVolumeArgs(C.Structure):
         ("groups", C.c_int32), ("eps_in_numerator", C.c_int32), ("variant", C.c_int32), ("reserved0", C.c_int32),
         ("feats", _f32p), ("pose", _f32p), ("hyps", _f32p), ("weights", _f32p), ("out", _f32p),
         ("out_stride_c", C.c_int64), ("out_stride_d", C.c_int64),
+        ("rays", _f32p),
     ]
 
 

@@ -116,7 +116,7 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
                     a->num_depth);
 
     SweepParams p;
-    p.feats = a->feats; p.pose = a->pose; p.hyps = a->hyps; p.weights = a->weights; p.out = a->out;
+    p.feats = a->feats; p.pose = a->pose; p.hyps = a->hyps; p.weights = a->weights; p.out = a->out; p.rays = a->rays;
     p.C = C; p.H = a->height; p.W = a->width; p.HW = a->height * a->width;
     p.out_sd = a->out_stride_d > 0 ? a->out_stride_d : p.HW;
     p.out_sc = a->out_stride_c > 0 ? a->out_stride_c : (long long)d_count * p.out_sd;

@@ -20,6 +20,7 @@ struct SweepParams {
     const float* __restrict__ pose;     // [V-1,4,4]
     const float* __restrict__ hyps;     // [D] or [D,H,W]
     const float* __restrict__ weights;  // [V-1,H,W] or null
+    const float* __restrict__ rays;     // [V-1,3,H*W] rot @ [x,y,1] per source view, or null (computed here)
     float* __restrict__ out;
     long long out_sc, out_sd;
     int C, H, W, HW;

@@ -101,6 +101,10 @@ __global__ void __launch_bounds__(256) sweep_base_kernel(const SweepParams p) {
         rx[v] = fmaf(m[2], 1.f, fmaf(m[1], (float)py, m[0] * (float)px));
         ry[v] = fmaf(m[6], 1.f, fmaf(m[5], (float)py, m[4] * (float)px));
         rz[v] = fmaf(m[10], 1.f, fmaf(m[9], (float)py, m[8] * (float)px));
+        if (p.rays) {   // the reference's own rot @ [x,y,1] (cuBLAS), whatever order it rounded in
+            const float* rr = p.rays + (size_t)(v) * 3 * p.HW + pix;
+            rx[v] = __ldg(rr); ry[v] = __ldg(rr + p.HW); rz[v] = __ldg(rr + 2 * (size_t)p.HW);
+        }
         tx[v] = m[3]; ty[v] = m[7]; tz[v] = m[11];
     }
 

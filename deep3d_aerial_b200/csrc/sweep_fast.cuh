@@ -135,6 +135,10 @@ __global__ void __launch_bounds__(256, (CPT == 4 ? 2 : 1)) sweep_fast_kernel(con
         rx[k] = fmaf(m[2], 1.f, fmaf(m[1], (float)py, m[0] * (float)px));
         ry[k] = fmaf(m[6], 1.f, fmaf(m[5], (float)py, m[4] * (float)px));
         rz[k] = fmaf(m[10], 1.f, fmaf(m[9], (float)py, m[8] * (float)px));
+        if (p.rays) {   // the reference's own rot @ [x,y,1] (cuBLAS), whatever order it rounded in
+            const float* rr = p.rays + (size_t)(v) * 3 * p.HW + pix;
+            rx[k] = __ldg(rr); ry[k] = __ldg(rr + p.HW); rz[k] = __ldg(rr + 2 * (size_t)p.HW);
+        }
         tx[k] = m[3]; ty[k] = m[7]; tz[k] = m[11];
     }
 

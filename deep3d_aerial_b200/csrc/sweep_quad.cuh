@@ -118,6 +118,10 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
             rx[i] = fmaf(m[2], 1.f, fmaf(m[1], (float)py, m[0] * (float)px));
             ry[i] = fmaf(m[6], 1.f, fmaf(m[5], (float)py, m[4] * (float)px));
             rz[i] = fmaf(m[10], 1.f, fmaf(m[9], (float)py, m[8] * (float)px));
+            if (p.rays) {   // the reference's own rot @ [x,y,1] (cuBLAS), whatever order it rounded in
+                const float* rr = p.rays + (size_t)(jview[i]) * 3 * p.HW + pix;
+                rx[i] = __ldg(rr); ry[i] = __ldg(rr + p.HW); rz[i] = __ldg(rr + 2 * (size_t)p.HW);
+            }
             tx[i] = m[3]; ty[i] = m[7]; tz[i] = m[11];
         }
         const float4 w = ldg4(p.feats + (size_t)pix * C + choff);

@@ -67,11 +67,45 @@ def relative_poses(proj: torch.Tensor) -> torch.Tensor:
     return torch.cat([torch.matmul(proj[i:i + 1], inv) for i in range(1, proj.shape[0])], 0).contiguous()
 
 
+_PIXEL_GRIDS = {}
+
+
+def _pixel_grid(h: int, w: int, device) -> torch.Tensor:
+    """[1,3,H*W] homogeneous pixel coordinates, built with the reference's calls (module.py:532-537)."""
+    key = (h, w, str(device))
+    if key not in _PIXEL_GRIDS:
+        y, x = torch.meshgrid([torch.arange(0, h, dtype=torch.float32, device=device),
+                               torch.arange(0, w, dtype=torch.float32, device=device)], indexing="ij")
+        y, x = y.contiguous().view(h * w), x.contiguous().view(h * w)
+        _PIXEL_GRIDS[key] = torch.unsqueeze(torch.stack((x, y, torch.ones_like(x))), 0)
+    return _PIXEL_GRIDS[key]
+
+
+def reference_rays(pose: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """[V-1,4,4] relative poses -> [V-1,3,H*W] = rot_i @ [x,y,1], by the reference's own call (module.py:538:
+    one [1,3,3] @ [1,3,H*W] torch.matmul per source view).
+
+    cuBLAS does not round this 3-term product the same way at every problem size: at H*W = 1376*928 (cascade
+    stage 2 of the 1856x2752 configuration) the columns past 2^20 - 32 leave the fma(r2,1,fma(r1,y,r0*x))
+    order it uses everywhere else (tools/diag_rays.py, diag_rays_n.py), which moves 5 % of those rays by an ulp
+    and the cost volume by 1e-4.  Handing the kernel the reference's own product makes the sampling
+    coordinates bit-identical whatever the library does."""
+    xyz = _pixel_grid(h, w, pose.device)
+    rays = torch.empty((pose.shape[0], 3, h * w), device=pose.device, dtype=torch.float32)
+    for i in range(pose.shape[0]):
+        torch.matmul(pose[i:i + 1, :3, :3], xyz, out=rays[i:i + 1])
+    return rays
+
+
 def cost_volume(texels: torch.Tensor, pose: torch.Tensor, hyps: torch.Tensor, mode: int = AGG_VARIANCE, *,
                 groups: int = 0, weights: Optional[torch.Tensor] = None, eps_in_numerator: bool = False,
                 d_begin: int = 0, d_count: int = 0, out: Optional[torch.Tensor] = None,
-                plane_major: bool = False, variant: int = 0) -> torch.Tensor:
+                plane_major: bool = False, variant: int = 0, rays: Optional[torch.Tensor] = None,
+                exact_rays: bool = True) -> torch.Tensor:
     """Fused warp + aggregate.  texels [V,H,W,C]; pose [V-1,4,4]; hyps [D] or [D,H,W].
+
+    rays: `reference_rays(pose, H, W)` if the caller already has them (plane-slice callers compute them once
+    per view); with exact_rays (default) they are computed here, with exact_rays=False the kernel forms them.
 
     Returns [Cout, Dn, H, W] (or [Dn, Cout, H, W] with plane_major=True, the layout whose planes are
     contiguous [Cout,H,W] slices for the plane-at-a-time regularisers), Dn = planes computed.
@@ -112,7 +146,14 @@ def cost_volume(texels: torch.Tensor, pose: torch.Tensor, hyps: torch.Tensor, mo
     a.mode, a.num_views, a.channels, a.height, a.width, a.num_depth = mode, v, c, h, w, d
     a.d_begin, a.d_count, a.hyps_per_pixel = d_begin, dn, per_pixel
     a.groups, a.eps_in_numerator, a.variant = groups, int(eps_in_numerator), variant
+    if rays is None and exact_rays:
+        rays = reference_rays(pose, h, w)
+    if rays is not None:
+        rays = _need(rays, "rays")
+        if tuple(rays.shape) != (v - 1, 3, h * w):
+            raise ValueError("rays must be [%d,3,%d], got %s" % (v - 1, h * w, tuple(rays.shape)))
     a.feats, a.pose, a.hyps, a.weights, a.out = texels.data_ptr(), pose.data_ptr(), hyps.data_ptr(), _ptr(weights), out.data_ptr()
+    a.rays = _ptr(rays)
     if plane_major:
         a.out_stride_c, a.out_stride_d = h * w, cout * h * w
     else:

@@ -79,6 +79,12 @@ typedef struct D3dCostVolumeArgs {
                                  + y*W + x]                                                       */
     int64_t out_stride_c;     /* elements; 0 selects the dense [Cout, d_count, H, W] layout        */
     int64_t out_stride_d;     /* elements; 0 selects H*W                                          */
+    const float* rays;        /* optional [V-1,3,H*W]: rot_i @ [x,y,1] for every reference pixel, i.e. the
+                                 result of module.py:538 computed by the caller with the reference's own
+                                 matmul.  NULL: the kernel forms the rays itself as
+                                 fma(r2,1,fma(r1,y,r0*x)), the order cuBLAS uses for most -- not all --
+                                 problem sizes (Numerics).  Passing them makes the sample
+                                 coordinates bit-identical to the reference's at every size           */
 } D3dCostVolumeArgs;
 
 /* Fused homography warp + bilinear sample + aggregation; the V x C x D x H x W warped volume is

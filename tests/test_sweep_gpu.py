@@ -452,6 +452,72 @@ def test_full_size_config_against_cuda_aten_on_plane_subsets(mode, kw):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("stage", [1, 2, 3])
+def test_full_size_cascade_stage_against_cuda_aten(stage):
+    """BASELINE.json config 3 (AdaMVS at 1856x2752): every stage's weighted-product volume (and stage 1's pair
+    volumes) at its production size and geometry -- 32 ch @ 688x464, 16 ch @ 1376x928, 8 ch @ 2752x1856, per-pixel
+    hypotheses -- checked on plane subsets against the reference's ATen path on this GPU."""
+    scale, c, d, ratio = {1: (4, 32, 48, 4), 2: (2, 16, 32, 2), 3: (1, 8, 8, 1)}[stage]
+    v = 5
+    rig = synth.make_rig(num_views=v)
+    h, w = 2752 // scale, 1856 // scale
+    g = torch.Generator().manual_seed(40 + stage)
+    feats = torch.randn(v, c, h, w, generator=g).to(DEV)
+    proj = torch.from_numpy(rig.proj(scale)).unsqueeze(0).to(DEV)
+    interval = ratio * (rig.dmax - rig.dmin) / 384
+    if stage == 1:
+        hyps = sweep.depth_samples(sweep.SAMPLES_RANGE, d, (h, w), device=torch.device(DEV), dmin=rig.dmin, dmax=rig.dmax)
+    else:
+        cur = synth.smooth_depth_map(rig, h, w, seed=stage).to(DEV)
+        hyps = sweep.depth_samples(sweep.SAMPLES_AROUND, d, (h, w), cur=cur, interval=interval)
+    weights = [torch.rand(1, 1, h, w, generator=g).to(DEV) for _ in range(v - 1)]
+    tex = sweep.to_texels(feats)
+    pose = sweep.relative_poses(proj[0])
+    wt = torch.cat(weights, 1)[0].contiguous()
+    vol = sweep.cost_volume(tex, pose, hyps, sweep.AGG_WEIGHTED_PRODUCT, weights=wt)
+    views = [feats[i:i + 1] for i in range(v)]
+    for d0 in sorted({0, d // 2, d - 2}):
+        sub = hyps[d0:d0 + 2].unsqueeze(0)
+        want = sweep_torch.weighted_product_volume(views, proj, sub, weights)[0]
+        err = rel_norm_err(vol[:, d0:d0 + 2], want)
+        print("stage %d weighted product planes %d..%d: rel err %.3e" % (stage, d0, d0 + 1, err))
+        assert err < VOL_TOL
+        del want
+    del vol
+    if stage == 1:
+        pairs = sweep.cost_volume(tex, pose, hyps, sweep.AGG_PAIR_MEAN)
+        for d0 in (0, 23, 46):
+            want = torch.stack(sweep_torch.pair_mean_volumes(views, proj, hyps[d0:d0 + 2].unsqueeze(0)), 1)[0]
+            assert rel_norm_err(pairs[:, d0:d0 + 2], want) < VOL_TOL
+
+
+def test_rays_from_the_reference_matmul_are_exact_at_every_size():
+    """cuBLAS rounds rot @ [x,y,1] differently past column 2^20 - 32 when H*W = 1376*928 (tools/diag_rays_n.py): the
+    kernel's own rays then differ from the reference's by an ulp in ~5 % of those columns (1.4e-4 on the variance
+    volume); with the reference's own product handed in (the default) the volume agrees to rounding noise.  At
+    sizes where the library keeps one order the two paths are bit-identical."""
+    rig = synth.make_rig(num_views=5)
+    h, w, c, d = 1376, 928, 16, 32
+    g = torch.Generator().manual_seed(11)
+    feats = torch.randn(5, c, h, w, generator=g).to(DEV)
+    proj = torch.from_numpy(rig.proj(2)).unsqueeze(0).to(DEV)
+    cur = synth.smooth_depth_map(rig, h, w, seed=2).to(DEV)
+    hyps = sweep.depth_samples(sweep.SAMPLES_AROUND, d, (h, w), cur=cur, interval=2 * (rig.dmax - rig.dmin) / 384)
+    tex, pose = sweep.to_texels(feats), sweep.relative_poses(proj[0])
+    want = sweep_torch.variance_volume([feats[i:i + 1] for i in range(5)], proj, hyps[3:5].unsqueeze(0))[0]
+    exact = sweep.cost_volume(tex, pose, hyps, sweep.AGG_VARIANCE, d_begin=3, d_count=2)
+    own = sweep.cost_volume(tex, pose, hyps, sweep.AGG_VARIANCE, d_begin=3, d_count=2, exact_rays=False)
+    err_exact, err_own = rel_norm_err(exact, want), rel_norm_err(own, want)
+    print("1376x928 variance: reference rays %.3e, kernel rays %.3e" % (err_exact, err_own))
+    assert err_exact < 1e-6
+    assert err_own < 5e-4                      # an ulp of coordinate on noise features, documented in DESIGN.md
+    _, proj2, feats2, hyps2 = _scene(5, 32, 8, 64, 48, seed=2)
+    tex2, pose2 = sweep.to_texels(feats2.to(DEV)), sweep.relative_poses(proj2[0].to(DEV))
+    a = sweep.cost_volume(tex2, pose2, hyps2[0].to(DEV), sweep.AGG_VARIANCE)
+    b = sweep.cost_volume(tex2, pose2, hyps2[0].to(DEV), sweep.AGG_VARIANCE, exact_rays=False)
+    assert rel_norm_err(a, b) < VOL_TOL
+
+
 def test_full_size_regression_against_cuda_aten():
     d, h, w = 384, 688, 464
     logits = synth.planted_logits(d, h, w, seed=1).to(DEV)

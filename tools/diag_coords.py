@@ -31,8 +31,10 @@ def frac(a, b, name):
 
 def main():
     rig = synth.make_rig(num_views=5)
-    h, w = 688, 464
-    proj = torch.from_numpy(rig.proj(4)).to(dev)
+    scale = int(sys.argv[1]) if len(sys.argv) > 1 else 4          # 4, 2, 1 = cascade stage 1, 2, 3
+    h, w = 2752 // scale, 1856 // scale
+    print("stage scale %d: %d x %d" % (scale, h, w))
+    proj = torch.from_numpy(rig.proj(scale)).to(dev)
     ref = proj[0:1]
     print("relative pose: batched matmul vs the reference's per-view [1,4,4] matmul")
     inv = torch.inverse(ref)
