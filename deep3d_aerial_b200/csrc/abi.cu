@@ -41,6 +41,8 @@ int sweep_quad_variance(int nv, const SweepParams& p, dim3 grid, cudaStream_t st
 int sweep_quad_group_corr(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_quad_weighted_product(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_quad_pair_mean(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
+int sweep_direct_variance(int nv, const SweepParams& p, cudaStream_t stream);
+int sweep_direct_weighted_product(int nv, const SweepParams& p, cudaStream_t stream);
 
 static int sm_count() {
     static int cached = 0;
@@ -153,6 +155,12 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
     // Shapes a kernel is not instantiated for fall through to the next one.
     int variant = a->variant;
     if (variant >= 16) { p.flags = variant - 16; variant = 0; }   // A/B switches of the production kernel
+    // 8-channel features (cascade stage 3): direct gather, one lane per pixel (sweep_direct.cuh)
+    if (variant == 0 && C == 8 && nv <= 4 && (a->mode == D3D_AGG_VARIANCE || a->mode == D3D_AGG_WEIGHTED_PRODUCT)) {
+        const int rc = a->mode == D3D_AGG_VARIANCE ? sweep_direct_variance(nv, p, stream)
+                                                   : sweep_direct_weighted_product(nv, p, stream);
+        if (rc >= 0) return rc;
+    }
     if (variant != 1 && a->mode == D3D_AGG_VARIANCE && nv <= 4) {
         const bool want8 = (variant == 3 || variant == 5) && C % 8 == 0;
         int fcpt = want8 ? 8 : 4;
