@@ -325,8 +325,11 @@ def test_pair_mean_matches_oracle(v, h, w):
     assert rel_norm_err(got, want) < VOL_TOL
 
 
-def test_plane_slices_and_plane_major_layout():
-    _, proj, feats, hyps = _scene(3, 8, 12, 40, 48, seed=9)
+@pytest.mark.parametrize("v,c,h,w", [(3, 8, 40, 48), (5, 32, 40, 48), (4, 16, 32, 64), (5, 32, 43, 29)])
+def test_plane_slices_and_plane_major_layout(v, c, h, w):
+    """Slice launches (the plane-at-a-time callers) and the plane-major layout reproduce the whole-volume launch
+    bit for bit on every kernel family (direct, quad with 8 / 4 lanes per pixel, lean)."""
+    _, proj, feats, hyps = _scene(v, c, 12, h, w, seed=9)
     full = _ours_volume(feats, proj, hyps, sweep.AGG_VARIANCE)
     part = _ours_volume(feats, proj, hyps, sweep.AGG_VARIANCE, d_begin=5, d_count=4)
     assert torch.equal(part, full[:, 5:9])
@@ -334,6 +337,8 @@ def test_plane_slices_and_plane_major_layout():
     assert torch.equal(pm.permute(1, 0, 2, 3), full)
     one = _ours_volume(feats, proj, hyps[:, 3:4], sweep.AGG_VARIANCE)           # D = 1
     assert torch.equal(one, full[:, 3:4])
+    for d0 in range(0, 12, 3):                                                   # three-plane slices, any phase
+        assert torch.equal(_ours_volume(feats, proj, hyps, sweep.AGG_VARIANCE, d_begin=d0, d_count=3), full[:, d0:d0 + 3])
 
 
 def test_points_behind_the_camera_contribute_zero():

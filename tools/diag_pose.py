@@ -1,7 +1,13 @@
-import sys, torch
-sys.path.insert(0, "/root/repo")
+"""Diagnostic (GPU box): are the relative poses bit-identical however the reference forms them?
+    python tools/diag_pose.py
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from deep3d_aerial_b200 import sweep, synth
-from oracle import sweep_torch
 torch.set_grad_enabled(False)
 dev = "cuda"
 rig = synth.make_rig(num_views=5)
