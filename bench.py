@@ -33,6 +33,7 @@ WORKLOADS = {
     # name: (V, C, D, H, W, mode, groups, description)
     "cfg1": (3, 8, 48, 128, 160, "variance", 0, "tiny variance V=3 C=8 D=48 128x160"),
     "cfg2": (5, 32, 384, 688, 464, "variance", 0, "WHU-OMVS V=5 C=32 D=384 688x464 (1/4 of 2752x1856) variance"),
+    "cfg2v3": (3, 32, 384, 688, 464, "variance", 0, "WHU-OMVS shape with V=3 (two source views): C=32 D=384 688x464 variance"),
     "cfg4": (5, 32, 384, 688, 464, "gwc", 8, "WHU-OMVS V=5 C=32 D=384 688x464 group-wise correlation G=8"),
 }
 

@@ -36,6 +36,7 @@ __device__ __forceinline__ float2 fadd2_rd(float2 a, float2 b) {       // packed
 }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 
+constexpr bool kQuadThreeCtas = true;   // <= 2 source views: 32 footprint registers, three CTAs per SM
 constexpr int kQuadPlanes = 4;       // planes per pass = planes per staged batch
 constexpr int kQuadBuffers = 4;      // staging ring
 
@@ -58,13 +59,14 @@ struct RefetchTok<NV, TEXB, NV> {
 // D3D_AGG_PAIR_MEAN writes one row per source view (mean over all channels of ref * warped).
 // GS: channels per group known at compile time (4 = the G=8 configuration of BASELINE.json), 0 = read p.groups.
 template <int NV, int MODE, bool kIeeeDiv, bool kPerPix, int GS = 0, int LPP = 8>
-__global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p) {
+__global__ void __launch_bounds__(256, (NV <= 2 && kQuadThreeCtas) ? 3 : 2) sweep_quad_kernel(const SweepParams p) {
     constexpr int CPT = 4, PPW = 32 / LPP, NP = 2, C = CPT * LPP;
     constexpr int PIX = 8 * PPW;                           // pixels per CTA: 32, 64 or 128
     constexpr int JPL = 8 / LPP;                           // projection chains a lane runs per pass
     constexpr int NVL = JPL > 1 ? JPL / 2 : 1;             // distinct views among them
     constexpr int KT = kQuadPlanes, NBUF = kQuadBuffers;
-    constexpr unsigned GEO_PLANE = 4 * PPW * 16;           // bytes: one plane's table of one warp (4 view slots)
+    constexpr int VS = NV <= 2 ? 2 : 4;                    // view slots of the table
+    constexpr unsigned GEO_PLANE = VS * PPW * 16;          // bytes: one plane's table of one warp
     constexpr unsigned GEO_BUF = KT * GEO_PLANE;
     constexpr unsigned TILE_PLANE = C * PIX * 4;           // bytes: one staged plane (4 KB whatever LPP)
     static_assert(MODE != D3D_AGG_PAIR_MEAN || LPP == 8, "pair-mean volumes are built from 32-channel features");
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(256, 2) sweep_quad_kernel(const SweepParams p)
 
 template <int NV, int MODE, int LPP>
 int launch_sweep_quad(const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div) {
-    const size_t smem = 64 + (size_t)8 * 2 * kQuadPlanes * 4 * (32 / LPP) * 16 +
+    const size_t smem = 64 + (size_t)8 * 2 * kQuadPlanes * (NV <= 2 ? 2 : 4) * (32 / LPP) * 16 +
                         (size_t)kQuadBuffers * kQuadPlanes * 32 * 32 * 4 +
                         (p.perpix ? 0 : (size_t)(p.d_chunk + kLeanHypPad) * 4);
     if (smem > 110 * 1024) return -1;                // keep two CTAs per SM; absurd depth chunks go elsewhere
