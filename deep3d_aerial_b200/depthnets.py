@@ -138,6 +138,14 @@ def red_infer_forward(self, features, proj_matrices, depth_values, num_depth, co
     state2 = torch.zeros((b_num, 16, int(img_h / 2), int(img_w / 2)), device=dev)
     state3 = torch.zeros((b_num, 32, int(img_h / 4), int(img_w / 4)), device=dev)
     state4 = torch.zeros((b_num, 64, int(img_h / 8), int(img_w / 8)), device=dev)
+    if PLANE_LOOP_GRAPHS and depth_values.dim() == 4:
+        loop = _plane_loop(self, "red", cost_regularization, b_num, num_depth, ref.shape[1], (img_h, img_w),
+                           (img_h, img_w), [tuple(s.shape) for s in (state1, state2, state3, state4)],
+                           tuple(depth_values.shape[2:]), dev)
+        _volume_into(loop.volume, features, proj_matrices, depth_values, sweep.AGG_VARIANCE)
+        loop.hyps.copy_(depth_values)
+        depth, conf = loop.replay()
+        return {"depth": depth.clone(), "photometric_confidence": conf.clone()}
     # all D variance planes in one launch, plane-major so each plane is a contiguous [C,H,W] slice
     volume = _volume(features, proj_matrices, depth_values, sweep.AGG_VARIANCE, plane_major=True)
     acc = _Stream(b_num, img_h, img_w, dev)

@@ -174,6 +174,39 @@ def test_plane_loop_graph_matches_eager(in_up):
     assert not torch.equal(outs[(True, 21)][0], outs[(True, 22)][0])
 
 
+class _RedLike(torch.nn.Module):
+    """Four-state recurrent stand-in with the signature of msrednet's slice regulariser."""
+
+    def forward(self, x, s1, s2, s3, s4):
+        pool = torch.nn.functional.avg_pool2d
+        s1 = torch.tanh(0.6 * s1 + 0.4 * x[:, :8])
+        s2 = 0.5 * s2 + 0.5 * pool(torch.cat([s1, s1], 1), 2)
+        s3 = 0.5 * s3 + 0.5 * pool(torch.cat([s2, s2], 1), 2)
+        s4 = 0.5 * s4 + 0.5 * pool(torch.cat([s3, s3], 1), 2)
+        up = torch.nn.functional.interpolate
+        logit = -2.0 * x.mean(1, keepdim=True) + s1.mean(1, keepdim=True) + up(s2.mean(1, keepdim=True), scale_factor=2) \
+            + up(s4.mean(1, keepdim=True), scale_factor=8)
+        return logit, s1, s2, s3, s4
+
+
+def test_red_plane_loop_graph_matches_eager():
+    v, c, d, h, w = 3, 8, 10, 32, 64
+    net, reg = object.__new__(type("Net", (), {})), _RedLike()
+    outs = {}
+    for graphs in (False, True):
+        depthnets.PLANE_LOOP_GRAPHS = graphs
+        try:
+            for seed in (31, 32):
+                _, proj, feats, hyps = _scene(v, c, d, h, w, seed=seed, perpixel=True)
+                out = depthnets.red_infer_forward(net, _cuda_views(feats), proj.to(DEV), hyps.to(DEV), d, reg)
+                outs[(graphs, seed)] = (out["depth"].clone(), out["photometric_confidence"].clone())
+        finally:
+            depthnets.PLANE_LOOP_GRAPHS = False
+    for seed in (31, 32):
+        assert torch.equal(outs[(True, seed)][0], outs[(False, seed)][0])
+        assert torch.equal(outs[(True, seed)][1], outs[(False, seed)][1])
+
+
 def test_adamvs_train_form_matches_golden():
     g = load_golden("ada_train_depthnet")
     w = g["pair_conf"][0, :, 0].to(DEV).contiguous()             # [V-1,h,w]
