@@ -123,36 +123,6 @@ def rebuild_lines(A, cpt):
             A("mov.b64 {%%%d, %%%d}, %s;" % (i, i + 1, reg))
 
 
-def block_rebuild(cpt):
-    n = 4 * cpt
-    mv, vplus1 = n, n + 1
-    L = []
-    A = L.append
-    A("{")
-    A(".reg .pred p;")
-    A(".reg .b32 t;")
-    A(".reg .b64 u0, u1, u2, u3;")
-    A("shr.u32 t, %%%d, %%%d;" % (mv, vplus1))
-    A("and.b32 t, t, 1;")
-    A("setp.eq.u32 p, t, 0;")
-    A("@p bra SAME;")
-    rebuild_lines(A, cpt)
-    A("SAME:")
-    A("}")
-    body = "\n        ".join('"%s\\n\\t"' % x for x in L)
-    ops = tex_operands(cpt)
-    outs = ",\n          ".join(", ".join(ops[i:i + 4]) for i in range(0, len(ops), 4))
-    return """// Split form, second half: corners -> A, B, C, D for the view whose bit is set in `moved`.
-template <int VPLUS1>
-__device__ __forceinline__ void rebuild_off(float2 (&t)[4][%d], unsigned moved) {
-    asm volatile(
-        %s
-        : %s
-        : "r"(moved), "n"(VPLUS1));
-}
-""" % (cpt // 2, body, outs)
-
-
 def block_off(cpt, split=False):
     """Offset-keyed re-fetch: the projection producer already turned the footprint into a byte offset, so the
     common (interior) case is two address adds, four loads and the packed rebuild."""
@@ -364,5 +334,5 @@ namespace d3d {
 
 if __name__ == "__main__":
     with open(OUT, "w") as f:
-        f.write(HEADER + block(8) + "\n" + block(4) + "\n" + block_off(8) + "\n" + block_off(4) + "\n" + block_off(8, True) + "\n" + block_off(4, True) + "\n" + block_rebuild(8) + "\n" + block_rebuild(4) + "\n" + block_tok(4) + "\n}  // namespace d3d\n")
+        f.write(HEADER + block(8) + "\n" + block(4) + "\n" + block_off(8) + "\n" + block_off(4) + "\n" + "\n" + block_tok(4) + "\n}  // namespace d3d\n")
     print("wrote", OUT)
