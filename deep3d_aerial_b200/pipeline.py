@@ -64,13 +64,16 @@ class ViewPipeline:
             s["feats"].copy_(feats, non_blocking=True)
             s["proj"].copy_(proj, non_blocking=True)
             s["hyps"].copy_(hyps, non_blocking=True)
+            # camera geometry of this view (the reference's own torch calls, module.py:528 and :538) also runs on
+            # the copy stream, i.e. behind the previous view's sweep; the slot keeps the tensors alive
+            s["pose"] = sweep.relative_poses(s["proj"])
+            s["rays"] = sweep.reference_rays(s["pose"], self.shape[2], self.shape[3])
             s["copied"].record()
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(s["copied"])
             sweep.to_texels(s["feats"], out=self.texels)
-            pose = sweep.relative_poses(s["proj"])
-            sweep.cost_volume(self.texels, pose, s["hyps"], self.mode, groups=self.groups, out=self.volume,
-                              variant=self.variant)
+            sweep.cost_volume(self.texels, s["pose"], s["hyps"], self.mode, groups=self.groups, out=self.volume,
+                              variant=self.variant, rays=s["rays"])
             logits = logits_fn(self.volume)
             r = sweep.depth_regress(logits, s["hyps"], conf_mode=self.conf_mode, want_index=False)
             s["free"].record()                                # inputs consumed: the slot may be refilled

@@ -556,6 +556,34 @@ def test_rays_from_the_reference_matmul_are_exact_at_every_size():
     assert rel_norm_err(a, b) < VOL_TOL
 
 
+def test_view_pipeline_matches_direct_calls():
+    """pipeline.ViewPipeline (pinned host in, pinned host out, two slots, copy + compute streams): five views through
+    two slots give what the synchronous calls give, bit for bit."""
+    from deep3d_aerial_b200.pipeline import ViewPipeline
+
+    v, c, d, h, w = 5, 32, 12, 40, 48
+    pipe = ViewPipeline(v, c, h, w, d, DEV)
+    views = []
+    for seed in range(5):
+        _, proj, feats, hyps = _scene(v, c, d, h, w, seed=50 + seed)
+        logits = synth.planted_logits(d, h, w, seed=seed).to(DEV)
+        views.append((feats.pin_memory(), proj[0].contiguous().pin_memory(), hyps[0].contiguous().pin_memory(), logits))
+    got = []
+    for i, (f, pr, hy, lg) in enumerate(views):
+        pipe.submit(f, pr, hy, lambda vol, lg=lg: lg)
+        if i:
+            dep, conf = pipe.collect()
+            got.append((dep.clone(), conf.clone()))
+    dep, conf = pipe.collect()
+    got.append((dep.clone(), conf.clone()))
+    for (f, pr, hy, lg), (dep, conf) in zip(views, got):
+        tex = sweep.to_texels(f.to(DEV))
+        sweep.cost_volume(tex, sweep.relative_poses(pr.to(DEV)), hy.to(DEV), sweep.AGG_VARIANCE)
+        r = sweep.depth_regress(lg, hy.to(DEV), want_index=False)
+        assert torch.equal(dep, r["depth"].cpu()) and torch.equal(conf, r["conf"].cpu())
+    assert pipe.h2d_bytes == 4 * (v * c * h * w + 16 * v + d) and pipe.d2h_bytes == 8 * h * w
+
+
 def test_full_size_regression_against_cuda_aten():
     d, h, w = 384, 688, 464
     logits = synth.planted_logits(d, h, w, seed=1).to(DEV)
