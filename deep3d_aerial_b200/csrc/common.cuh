@@ -34,6 +34,23 @@ struct SweepParams {
     float wm1, hm1;                // W-1, H-1                   (GridSampler.h:27-32)
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember the size each kernel was opted
+// into per device, so a process that drives several GPUs (or several host threads) configures every one of them.
+constexpr int kMaxDevices = 64;
+struct SmemOptIn {
+    size_t bytes[kMaxDevices] = {};
+    template <typename Kernel>
+    int ensure(Kernel kern, size_t smem) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+        if (bytes[dev] >= smem) return D3D_OK;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(D3D_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+        bytes[dev] = smem;
+        return D3D_OK;
+    }
+};
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 }  // namespace d3d

@@ -355,12 +355,8 @@ template <int CPT, int NV, int LPP, int MODE>
 int launch_sweep_fast(const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div) {
     constexpr size_t smem = sweep_fast_smem<CPT, NV, LPP>();
     auto kern = ieee_div ? sweep_fast_kernel<CPT, NV, LPP, MODE, true> : sweep_fast_kernel<CPT, NV, LPP, MODE, false>;
-    static bool configured[2] = {false, false};      // per instantiation, per division flavour
-    if (!configured[ieee_div]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(D3D_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
-        configured[ieee_div] = true;
-    }
+    static SmemOptIn opted[2];                       // per instantiation, per division flavour
+    if (int rc = opted[ieee_div].ensure(kern, smem)) return rc;
     kern<<<grid, 256, smem, stream>>>(p);
     count_launch();
     return check_launch("sweep_fast_kernel");

@@ -427,12 +427,8 @@ int launch_sweep_lean(const SweepParams& p, dim3 grid, cudaStream_t stream, bool
         case 2: kern = sweep_lean_kernel<CPT, NV, LPP, MODE, true, false>; break;
         default: kern = sweep_lean_kernel<CPT, NV, LPP, MODE, true, true>; break;
     }
-    static size_t configured[4] = {0, 0, 0, 0};      // per instantiation and flavour: largest size set so far
-    if (configured[which] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(D3D_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
-        configured[which] = smem;
-    }
+    static SmemOptIn opted[4];                       // per instantiation and flavour
+    if (int rc = opted[which].ensure(kern, smem)) return rc;
     kern<<<grid, 256, smem, stream>>>(p);
     count_launch();
     return check_launch("sweep_lean_kernel");

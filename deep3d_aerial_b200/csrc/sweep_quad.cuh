@@ -461,13 +461,8 @@ int launch_sweep_quad(const SweepParams& p, dim3 grid, cudaStream_t stream, bool
         case 2: kern = sweep_quad_kernel<NV, MODE, true, false, 0, LPP>; break;
         default: kern = sweep_quad_kernel<NV, MODE, true, true, 0, LPP>; break;
     }
-    static size_t configured_all[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-    size_t* configured = configured_all[g8 ? 1 : 0];
-    if (configured[which] < smem_req) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req);
-        if (e != cudaSuccess) return fail(D3D_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem_req, cudaGetErrorString(e));
-        configured[which] = smem_req;
-    }
+    static SmemOptIn opted[2][4];                    // per instantiation, group flavour and kernel flavour
+    if (int rc = opted[g8 ? 1 : 0][which].ensure(kern, smem_req)) return rc;
     kern<<<grid, 256, smem_req, stream>>>(p);
     count_launch();
     return check_launch("sweep_quad_kernel");

@@ -584,6 +584,20 @@ def test_view_pipeline_matches_direct_calls():
     assert pipe.h2d_bytes == 4 * (v * c * h * w + 16 * v + d) and pipe.d2h_bytes == 8 * h * w
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_one_process_two_devices():
+    """The shared-memory opt-in of the sweep kernels is a per-device attribute: a process that drives a second
+    GPU after the first must get the same volumes there."""
+    _, proj, feats, hyps = _scene(5, 32, 12, 64, 48, seed=3)
+    outs = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        with torch.cuda.device(dev):
+            tex = sweep.to_texels(feats.to(dev))
+            pose = sweep.relative_poses(proj[0].to(dev))
+            outs.append(sweep.cost_volume(tex, pose, hyps[0].to(dev), sweep.AGG_VARIANCE).cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
 def test_full_size_regression_against_cuda_aten():
     d, h, w = 384, 688, 464
     logits = synth.planted_logits(d, h, w, seed=1).to(DEV)
