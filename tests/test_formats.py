@@ -147,7 +147,7 @@ def test_predict_driver_writes_the_reference_outputs(workspace, tmp_path):
     import torch.nn as nn
     import torch.nn.functional as F
 
-    from deep3d_aerial_b200 import depthnets, predict
+    from deep3d_aerial_b200 import depthnets, module as d3d_module, predict
     from oracle import standins, sweep_torch
 
     class TinyCascade(nn.Module):                          # one stage at 1/4 resolution, 8 fixed "feature" channels
@@ -163,9 +163,9 @@ def test_predict_driver_writes_the_reference_outputs(workspace, tmp_path):
 
         def forward(self, imgs, proj_matrices, depth_values):
             feats = self.features(imgs)
-            proj = torch.unbind(proj_matrices["stage1"], 1)
+            proj = proj_matrices["stage1"]
             h, w = feats[0].shape[2:]
-            hyps = depthnets.module.get_depth_range_samples(depth_values, self.num_depth, 1.0, imgs.device, imgs.dtype,
+            hyps = d3d_module.get_depth_range_samples(depth_values, self.num_depth, 1.0, imgs.device, imgs.dtype,
                                                             [imgs.shape[0], h, w])
             out = self.depthnet(feats, proj, hyps, self.num_depth, standins.reg3d)
             return {"depth": out["depth"], "photometric_confidence": out["photometric_confidence"], "hyps": hyps,
