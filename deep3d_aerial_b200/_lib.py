@@ -58,10 +58,30 @@ class SamplesArgs(C.Structure):
     ]
 
 
+FUSE_MAX_SRC, FUSE_GEOM_DOUBLES = 16, 64
+
+
+class FuseArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("num_src", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("src_height", C.c_int32), ("src_width", C.c_int32), ("min_consistent", C.c_int32), ("reserved0", C.c_int32),
+        ("position_threshold", C.c_double),
+        ("depth_threshold", C.c_float), ("confidence_threshold", C.c_float), ("normal_threshold_cos", C.c_float),
+        ("reserved1", C.c_int32),
+        ("depth_ref", _f32p), ("normal_ref", _f32p), ("prob_ref", _f32p), ("geometry", C.c_void_p),
+        ("depth_src", C.c_void_p * FUSE_MAX_SRC), ("normal_src", C.c_void_p * FUSE_MAX_SRC),
+        ("depth_src_out", C.c_void_p * FUSE_MAX_SRC),
+        ("mask", C.c_void_p), ("depth_reprojected", _f32p), ("xyz_world_src", _f32p), ("angle_conf", _f32p),
+        ("consistent_count", C.c_void_p), ("xyz_fused", _f32p), ("final_mask", C.c_void_p),
+        ("depth_ref_filtered", _f32p),
+    ]
+
+
 EXPORTS = {
     "d3d_cost_volume": (C.c_int, [C.POINTER(CostVolumeArgs), C.c_void_p]),
     "d3d_depth_regress": (C.c_int, [C.POINTER(RegressArgs), C.c_void_p]),
     "d3d_depth_samples": (C.c_int, [C.POINTER(SamplesArgs), C.c_void_p]),
+    "d3d_consistency_fuse": (C.c_int, [C.POINTER(FuseArgs), C.c_void_p]),
     "d3d_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "d3d_last_error": (C.c_char_p, []),
     "d3d_version": (C.c_int, []),
@@ -93,7 +113,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = restype
             fn.argtypes = argtypes
-        for which, struct in enumerate((CostVolumeArgs, RegressArgs, SamplesArgs)):
+        for which, struct in enumerate((CostVolumeArgs, RegressArgs, SamplesArgs, FuseArgs)):
             if lib.d3d_abi_sizeof(which) != C.sizeof(struct):
                 raise ImportError("ABI mismatch: %s is %d bytes here, %d in libd3dsweep.so"
                                   % (struct.__name__, C.sizeof(struct), lib.d3d_abi_sizeof(which)))

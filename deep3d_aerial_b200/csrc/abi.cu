@@ -73,6 +73,7 @@ extern "C" int32_t d3d_abi_sizeof(int32_t which) {
         case 0: return (int32_t)sizeof(D3dCostVolumeArgs);
         case 1: return (int32_t)sizeof(D3dRegressArgs);
         case 2: return (int32_t)sizeof(D3dSamplesArgs);
+        case 3: return (int32_t)sizeof(D3dFuseArgs);
         default: return -1;
     }
 }

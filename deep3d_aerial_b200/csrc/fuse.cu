@@ -1,0 +1,208 @@
+// Depth-map fusion: geometric consistency of one reference view against all its source views, one launch.
+//
+// Stands in for ConsistencyChecker.check_cupy (fuse/consistency_check_n.py:29-138: ~25 CuPy launches, a host-side
+// meshgrid and 9 host->device + 5 device->host copies per SOURCE view) and for the accumulation loop around it
+// (fuse/fusion_3d_normal.py:436-536).  One thread per reference pixel, consecutive lanes = consecutive x: the
+// reference maps are read once, coalesced; neighbouring pixels project to neighbouring source pixels, so the
+// gathers of a warp fall into a handful of 128-byte lines.  Points are fp64 and normals fp32 -- the types the
+// reference's own promotion rules produce (int64 grid x fp32 depth -> fp64; fp32 rotation x fp32 normal -> fp32).
+// Bound: HBM (20 B per reference pixel + 16 B gathered and <= 33 B written per pixel and source view).
+#include "common.cuh"
+
+namespace d3d {
+
+constexpr int kFuseThreads = 256;
+constexpr int kGeom = D3D_FUSE_GEOM_DOUBLES;
+
+struct FuseParams {
+    const float* __restrict__ depth_ref;
+    const float* __restrict__ normal_ref;
+    const float* __restrict__ prob_ref;
+    const double* __restrict__ geometry;
+    const float* depth_src[D3D_FUSE_MAX_SRC];
+    const float* normal_src[D3D_FUSE_MAX_SRC];
+    float* depth_src_out[D3D_FUSE_MAX_SRC];
+    uint8_t* __restrict__ mask;
+    float* __restrict__ depth_reprojected;
+    float* __restrict__ xyz_world_src;
+    float* __restrict__ angle_conf;
+    int32_t* __restrict__ consistent_count;
+    float* __restrict__ xyz_fused;
+    uint8_t* __restrict__ final_mask;
+    float* __restrict__ depth_ref_filtered;
+    double position_threshold;
+    float depth_threshold, confidence_threshold, normal_threshold_cos;
+    int S, H, W, Hs, Ws, min_consistent;
+};
+
+// row-major 3x3 times a 3-vector / 3 rows of a 4x4 times [v;w]
+__device__ __forceinline__ void mat3(const double* m, double a, double b, double c, double& x, double& y, double& z) {
+    x = m[0] * a + m[1] * b + m[2] * c;
+    y = m[3] * a + m[4] * b + m[5] * c;
+    z = m[6] * a + m[7] * b + m[8] * c;
+}
+__device__ __forceinline__ double row4(const double* r, double a, double b, double c, double w) {
+    return r[0] * a + r[1] * b + r[2] * c + r[3] * w;
+}
+// fp32 rotation of an fp32 normal (np.matmul of two float32 arrays stays float32)
+__device__ __forceinline__ void rot3f(const double* m, float a, float b, float c, float& x, float& y, float& z) {
+    x = (float)m[0] * a + (float)m[1] * b + (float)m[2] * c;
+    y = (float)m[3] * a + (float)m[4] * b + (float)m[5] * c;
+    z = (float)m[6] * a + (float)m[7] * b + (float)m[8] * c;
+}
+// Python-style modulo: CuPy wraps out-of-bounds integer-array indices around the axis
+__device__ __forceinline__ long long wrap(long long i, int n) {
+    long long r = i % n;
+    return r < 0 ? r + n : r;
+}
+
+__global__ void __launch_bounds__(kFuseThreads) consistency_fuse_kernel(const FuseParams p) {
+    extern __shared__ double geo[];                        // (1 + S) blocks of kGeom doubles
+    for (int i = threadIdx.x; i < (1 + p.S) * kGeom; i += kFuseThreads) geo[i] = __ldg(p.geometry + i);
+    __syncthreads();
+
+    const long long hw = (long long)p.H * p.W;
+    const long long pix = (long long)blockIdx.x * kFuseThreads + threadIdx.x;
+    if (pix >= hw) return;
+    const int y = (int)(pix / p.W), x = (int)(pix - (long long)y * p.W);
+
+    const float d = __ldg(p.depth_ref + pix);
+    const float prob = __ldg(p.prob_ref + pix);
+    const float n0 = __ldg(p.normal_ref + 3 * pix), n1 = __ldg(p.normal_ref + 3 * pix + 1),
+                n2 = __ldg(p.normal_ref + 3 * pix + 2);
+    const double dd = (double)d;
+    const double* G0 = geo;
+    double px, py, pz;                                     // reference camera space (:51-53)
+    mat3(G0, (double)x * dd, (double)y * dd, dd, px, py, pz);
+    float nrx, nry, nrz;                                   // reference normal in the world (:104-106)
+    rot3f(G0 + 46, n0, n1, n2, nrx, nry, nrz);
+    // numpy rounds every product before it adds (np.sum(a*b), np.linalg.norm): no FMA contraction on these
+    auto dot3 = [](float a0, float a1, float a2, float b0, float b1, float b2) {
+        return __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
+    };
+    const float nr_norm = sqrtf(dot3(nrx, nry, nrz, nrx, nry, nrz));
+
+    // accumulators of fusion_3d_normal.py:449-455, 525-527: world point of the reference pixel, confidence 1
+    float ax = (float)row4(G0 + 30, px, py, pz, 1.0), ay = (float)row4(G0 + 34, px, py, pz, 1.0),
+          az = (float)row4(G0 + 38, px, py, pz, 1.0);
+    float aconf = 1.f;
+    int count = 1;
+    const bool gate = prob > p.confidence_threshold && d > 0.f;
+
+    for (int s = 0; s < p.S; ++s) {
+        const double* G = geo + (1 + s) * kGeom;
+        // source camera space and pixel (:56-72)
+        const double qx = row4(G, px, py, pz, 1.0), qy = row4(G + 4, px, py, pz, 1.0), qz = row4(G + 8, px, py, pz, 1.0);
+        double kx, ky, kz;
+        mat3(G + 12, qx, qy, qz, kx, ky, kz);
+        const long long xs = __double2ll_rz(kx / kz + 0.5), ys = __double2ll_rz(ky / kz + 0.5);
+        const long long at = wrap(ys, p.Hs) * p.Ws + wrap(xs, p.Ws);
+        const float sd = __ldg(p.depth_src[s] + at);
+        const float* np_ = p.normal_src[s] + 3 * at;
+        const float m0 = __ldg(np_), m1 = __ldg(np_ + 1), m2 = __ldg(np_ + 2);
+        // back to the source camera, the world, the reference camera (:76-92)
+        const double sdd = (double)sd;
+        double cx, cy, cz;
+        mat3(G + 21, (double)xs * sdd, (double)ys * sdd, sdd, cx, cy, cz);
+        const double wx = row4(G + 30, cx, cy, cz, 1.0), wy = row4(G + 34, cx, cy, cz, 1.0),
+                     wz = row4(G + 38, cx, cy, cz, 1.0), ww = row4(G + 42, cx, cy, cz, 1.0);
+        const double rx = row4(G0 + 9, wx, wy, wz, ww), ry = row4(G0 + 13, wx, wy, wz, ww),
+                     rz = row4(G0 + 17, wx, wy, wz, ww);
+        const float depth_rep = (float)rz;
+        double ux, uy, uz;
+        mat3(G0 + 21, rx, ry, rz, ux, uy, uz);
+        const float xr = (float)(ux / uz), yr = (float)(uy / uz);
+        // position (fp32 pixel minus int64 grid -> fp64), depth (fp32), normal (fp32) tests (:95-123)
+        const double ex = (double)xr - (double)x, ey = (double)yr - (double)y;
+        const double dist = sqrt(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)));
+        const float rel = __fdiv_rn(fabsf(depth_rep - d), d);
+        float nsx, nsy, nsz;
+        rot3f(G + 46, m0, m1, m2, nsx, nsy, nsz);
+        const float cosv = __fdiv_rn(dot3(nrx, nry, nrz, nsx, nsy, nsz),
+                                     __fmul_rn(nr_norm, sqrtf(dot3(nsx, nsy, nsz, nsx, nsy, nsz))));
+        const bool ok = gate && dist < p.position_threshold && rel < p.depth_threshold && cosv > p.normal_threshold_cos;
+
+        const float conf = ok ? fmaxf(cosv, 0.f) : 0.f;
+        const float fx = ok ? (float)wx : 0.f, fy = ok ? (float)wy : 0.f, fz = ok ? (float)wz : 0.f;
+        if (ok) {
+            ++count;
+            ax = __fadd_rn(ax, __fmul_rn(conf, fx));                // (angle_conf * xyz).astype(float32), :526
+            ay = __fadd_rn(ay, __fmul_rn(conf, fy));
+            az = __fadd_rn(az, __fmul_rn(conf, fz));
+            aconf += conf;
+            if (p.depth_src_out[s]) p.depth_src_out[s][at] = 0.f;   // consumed by this reference view (:128-131)
+        }
+        const long long o = (long long)s * hw + pix;
+        if (p.mask) p.mask[o] = ok;
+        if (p.depth_reprojected) p.depth_reprojected[o] = ok ? depth_rep : 0.f;
+        if (p.angle_conf) p.angle_conf[o] = conf;
+        if (p.xyz_world_src) {
+            float* q = p.xyz_world_src + (long long)s * 3 * hw + pix;
+            q[0] = fx; q[hw] = fy; q[2 * hw] = fz;
+        }
+    }
+    const bool keep = count >= p.min_consistent;
+    if (p.consistent_count) p.consistent_count[pix] = count;
+    if (p.final_mask) p.final_mask[pix] = keep;
+    if (p.depth_ref_filtered) p.depth_ref_filtered[pix] = keep ? d : 0.f;
+    if (p.xyz_fused) {
+        p.xyz_fused[pix] = __fdiv_rn(ax, aconf);
+        p.xyz_fused[hw + pix] = __fdiv_rn(ay, aconf);
+        p.xyz_fused[2 * hw + pix] = __fdiv_rn(az, aconf);
+    }
+}
+
+}  // namespace d3d
+
+using namespace d3d;
+
+extern "C" int d3d_consistency_fuse(const D3dFuseArgs* a, void* cuda_stream) {
+    if (!a) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_consistency_fuse: args is NULL");
+    if (a->struct_size != sizeof(D3dFuseArgs))
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_consistency_fuse: struct_size %u != %zu", a->struct_size, sizeof(D3dFuseArgs));
+    if (a->num_src < 1 || a->num_src > D3D_FUSE_MAX_SRC)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_consistency_fuse: num_src %d outside 1..%d", a->num_src, D3D_FUSE_MAX_SRC);
+    if (a->height < 1 || a->width < 1 || a->src_height < 1 || a->src_width < 1)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_consistency_fuse: bad extent %dx%d / %dx%d", a->height, a->width,
+                    a->src_height, a->src_width);
+    if (!a->depth_ref || !a->normal_ref || !a->prob_ref || !a->geometry)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_consistency_fuse: depth_ref/normal_ref/prob_ref/geometry is NULL");
+    for (int s = 0; s < a->num_src; ++s) {
+        if (!a->depth_src[s] || !a->normal_src[s])
+            return fail(D3D_ERR_BAD_ARGUMENT, "d3d_consistency_fuse: depth_src[%d]/normal_src[%d] is NULL", s, s);
+        if (a->depth_src_out[s] && a->depth_src_out[s] == a->depth_src[s])
+            return fail(D3D_ERR_BAD_ARGUMENT, "d3d_consistency_fuse: depth_src_out[%d] aliases depth_src[%d] (the gathers "
+                        "of one pixel would race with the zeroing of another)", s, s);
+    }
+    const long long hw = (long long)a->height * a->width;
+    if (hw > (1LL << 31) - kFuseThreads) return fail(D3D_ERR_UNSUPPORTED, "d3d_consistency_fuse: H*W too large");
+
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    FuseParams p;
+    p.depth_ref = a->depth_ref; p.normal_ref = a->normal_ref; p.prob_ref = a->prob_ref; p.geometry = a->geometry;
+    const size_t src_bytes = (size_t)a->src_height * a->src_width * sizeof(float);
+    for (int s = 0; s < D3D_FUSE_MAX_SRC; ++s) {
+        const bool on = s < a->num_src;
+        p.depth_src[s] = on ? a->depth_src[s] : nullptr;
+        p.normal_src[s] = on ? a->normal_src[s] : nullptr;
+        p.depth_src_out[s] = on ? a->depth_src_out[s] : nullptr;
+        if (on && a->depth_src_out[s]) {
+            cudaError_t e = cudaMemcpyAsync(a->depth_src_out[s], a->depth_src[s], src_bytes, cudaMemcpyDeviceToDevice, stream);
+            if (e != cudaSuccess) return fail(D3D_ERR_CUDA, "d3d_consistency_fuse: copy of depth_src[%d]: %s", s, cudaGetErrorString(e));
+        }
+    }
+    p.mask = a->mask; p.depth_reprojected = a->depth_reprojected; p.xyz_world_src = a->xyz_world_src;
+    p.angle_conf = a->angle_conf; p.consistent_count = a->consistent_count; p.xyz_fused = a->xyz_fused;
+    p.final_mask = a->final_mask; p.depth_ref_filtered = a->depth_ref_filtered;
+    p.position_threshold = a->position_threshold;
+    p.depth_threshold = a->depth_threshold; p.confidence_threshold = a->confidence_threshold;
+    p.normal_threshold_cos = a->normal_threshold_cos;
+    p.S = a->num_src; p.H = a->height; p.W = a->width; p.Hs = a->src_height; p.Ws = a->src_width;
+    p.min_consistent = a->min_consistent;
+
+    const unsigned blocks = (unsigned)((hw + kFuseThreads - 1) / kFuseThreads);
+    const size_t smem = (size_t)(1 + a->num_src) * kGeom * sizeof(double);
+    consistency_fuse_kernel<<<blocks, kFuseThreads, smem, stream>>>(p);
+    count_launch();
+    return check_launch("consistency_fuse_kernel");
+}

@@ -1,0 +1,151 @@
+"""Depth-map fusion consistency check on the B200: the reference's
+`fuse/consistency_check_n.py` call surface over `d3d_consistency_fuse` (include/d3d_sweep.h).
+
+    ConsistencyChecker(position_threshold, depth_threshold, normal_threshold, confidence_threshold, implement)
+        .check(depth_ref, normal_ref, intrinsics_ref, extrinsics_ref, depth_src, normal_src, intrinsics_src,
+               extrinsics_src, prob_map_ref) -> (mask, depth_reprojected, depth_src, xyz_world_src, angle_confidence)
+                                                 numpy arrays, as upstream (consistency_check_n.py:17-148)
+    fuse_view(...)   one launch for a reference view and ALL its source views, device tensors in and out: what
+                     the loop of Fuse_Depth_Map.fuse_depths accumulates (fuse/fusion_3d_normal.py:436-541)
+
+The small matrices (inverses and products of K and Tcw) are formed on the host with the reference's own numpy
+calls in the matrices' own dtype and handed to the kernel as fp64 (`pair_geometry`); everything per pixel runs in
+one CUDA kernel.  No CPU fallback: a missing library or CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MAX_SRC = _lib.FUSE_MAX_SRC
+
+
+def pair_geometry(intrinsics_ref, extrinsics_ref, intrinsics_src: Sequence, extrinsics_src: Sequence) -> np.ndarray:
+    """[(1+S), 64] float64: the matrices `d3d_consistency_fuse` needs (layout in include/d3d_sweep.h), each
+    computed as the reference computes it (consistency_check_n.py:52, 56, 76, 80, 103, 107;
+    fusion_3d_normal.py:449-451)."""
+    k_ref, e_ref = np.asarray(intrinsics_ref), np.asarray(extrinsics_ref)
+    g = np.zeros((1 + len(intrinsics_src), _lib.FUSE_GEOM_DOUBLES), dtype=np.float64)
+    e_ref_inv = np.linalg.inv(e_ref)
+    g[0, 0:9] = np.linalg.inv(k_ref).reshape(-1)
+    g[0, 9:21] = e_ref[:3, :4].reshape(-1)
+    g[0, 21:30] = k_ref.reshape(-1)
+    g[0, 30:46] = e_ref_inv.reshape(-1)
+    g[0, 46:55] = np.linalg.inv(e_ref[:3, :3]).reshape(-1)
+    for s, (k, e) in enumerate(zip(intrinsics_src, extrinsics_src)):
+        k, e = np.asarray(k), np.asarray(e)
+        g[1 + s, 0:12] = np.matmul(e, e_ref_inv)[:3, :4].reshape(-1)
+        g[1 + s, 12:21] = k.reshape(-1)
+        g[1 + s, 21:30] = np.linalg.inv(k).reshape(-1)
+        g[1 + s, 30:46] = np.linalg.inv(e).reshape(-1)
+        g[1 + s, 46:55] = np.linalg.inv(e[:3, :3]).reshape(-1)
+    return g
+
+
+def _dev(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (libd3dsweep has no CPU fallback)" % name)
+    if t.dtype != dtype or not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous %s, got %s" % (name, dtype, t.dtype))
+    return t
+
+
+def fuse_view(depth_ref, normal_ref, prob_ref, geometry, depth_src, normal_src, *, position_threshold=1.0,
+              depth_threshold=0.01, normal_threshold_cos=0.0, confidence_threshold=0.2, min_consistent=4,
+              per_source=False, update_sources=True, out: Optional[dict] = None) -> dict:
+    """One reference view against S <= 16 source views, one kernel launch on the current stream.
+
+    depth_ref [H,W], normal_ref [H,W,3], prob_ref [H,W]; depth_src / normal_src: lists of S tensors [Hs,Ws] /
+    [Hs,Ws,3]; geometry: `pair_geometry(...)` as a CUDA float64 tensor.  Returns device tensors:
+      count [H,W] int32, xyz [3,H,W], final_mask [H,W] bool, depth_ref_filtered [H,W], masks [S,H,W] bool,
+      depth_src_out (list of S maps with the consumed pixels zeroed; `update_sources=False` skips them) and, with
+      `per_source`, depth_reprojected [S,H,W], xyz_world_src [S,3,H,W], angle_conf [S,H,W].
+    `out` may carry preallocated tensors under the same keys."""
+    lib = _lib.load()
+    s_n = len(depth_src)
+    if not 1 <= s_n <= MAX_SRC or len(normal_src) != s_n:
+        raise ValueError("need 1..%d source views with a normal map each, got %d / %d" % (MAX_SRC, s_n, len(normal_src)))
+    _dev(depth_ref, "depth_ref"), _dev(normal_ref, "normal_ref"), _dev(prob_ref, "prob_ref")
+    _dev(geometry, "geometry", torch.float64)
+    h, w = depth_ref.shape
+    hs, ws = depth_src[0].shape
+    if tuple(normal_ref.shape) != (h, w, 3) or tuple(prob_ref.shape) != (h, w):
+        raise ValueError("normal_ref / prob_ref do not match depth_ref %dx%d" % (h, w))
+    if geometry.numel() != (1 + s_n) * _lib.FUSE_GEOM_DOUBLES:
+        raise ValueError("geometry holds %d doubles, expected %d" % (geometry.numel(), (1 + s_n) * _lib.FUSE_GEOM_DOUBLES))
+    dev = depth_ref.device
+    out = dict(out or {})
+
+    def buf(key, shape, dtype):
+        t = out.get(key)
+        if t is None:
+            t = out[key] = torch.empty(shape, device=dev, dtype=dtype)
+        return _dev(t, key, dtype)
+
+    a = _lib.FuseArgs()
+    a.struct_size = C.sizeof(a)
+    a.num_src, a.height, a.width, a.src_height, a.src_width = s_n, h, w, hs, ws
+    a.min_consistent = int(min_consistent)
+    a.position_threshold = float(position_threshold)
+    a.depth_threshold, a.confidence_threshold = float(depth_threshold), float(confidence_threshold)
+    a.normal_threshold_cos = float(normal_threshold_cos)
+    a.depth_ref, a.normal_ref, a.prob_ref = depth_ref.data_ptr(), normal_ref.data_ptr(), prob_ref.data_ptr()
+    a.geometry = geometry.data_ptr()
+    if update_sources and "depth_src_out" not in out:
+        out["depth_src_out"] = [torch.empty_like(d) for d in depth_src]
+    for s in range(s_n):
+        if tuple(depth_src[s].shape) != (hs, ws) or tuple(normal_src[s].shape) != (hs, ws, 3):
+            raise ValueError("source %d: maps must all be %dx%d" % (s, hs, ws))
+        a.depth_src[s] = _dev(depth_src[s], "depth_src[%d]" % s).data_ptr()
+        a.normal_src[s] = _dev(normal_src[s], "normal_src[%d]" % s).data_ptr()
+        if update_sources:
+            a.depth_src_out[s] = _dev(out["depth_src_out"][s], "depth_src_out[%d]" % s).data_ptr()
+    a.mask = buf("masks", (s_n, h, w), torch.bool).data_ptr()
+    a.consistent_count = buf("count", (h, w), torch.int32).data_ptr()
+    a.xyz_fused = buf("xyz", (3, h, w), torch.float32).data_ptr()
+    a.final_mask = buf("final_mask", (h, w), torch.bool).data_ptr()
+    a.depth_ref_filtered = buf("depth_ref_filtered", (h, w), torch.float32).data_ptr()
+    if per_source:
+        a.depth_reprojected = buf("depth_reprojected", (s_n, h, w), torch.float32).data_ptr()
+        a.xyz_world_src = buf("xyz_world_src", (s_n, 3, h, w), torch.float32).data_ptr()
+        a.angle_conf = buf("angle_conf", (s_n, h, w), torch.float32).data_ptr()
+    _lib.check(lib.d3d_consistency_fuse(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out
+
+
+class ConsistencyChecker(object):
+    """Drop-in for `fuse/consistency_check_n.py:ConsistencyChecker`: same constructor, same `check` signature,
+    numpy arrays in and out.  `implement` is accepted for compatibility (upstream asserts it is one of
+    numpy / cupy / torch and always runs CuPy); here every call runs the CUDA kernel on the current device."""
+
+    def __init__(self, position_threshold, depth_threshold, normal_threshold, confidence_threshold, implement="cupy"):
+        self.position_threshold = position_threshold
+        self.depth_threshold = depth_threshold
+        self.normal_threshold = math.cos(math.radians(normal_threshold))
+        self.confidence_threshold = confidence_threshold
+        print("normal_th:" + str(self.normal_threshold))
+        self.implement = implement.lower()
+        assert self.implement in ["numpy", "cupy", "torch"]
+        _lib.load()
+
+    def check(self, depth_ref, normal_ref, intrinsics_ref, extrinsics_ref, depth_src, normal_src, intrinsics_src,
+              extrinsics_src, prob_map_ref):
+        dev = torch.device("cuda", torch.cuda.current_device())
+
+        def up(x):
+            return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dev)
+
+        geom = torch.from_numpy(pair_geometry(intrinsics_ref, extrinsics_ref, [intrinsics_src], [extrinsics_src])).to(dev)
+        r = fuse_view(up(depth_ref), up(normal_ref), up(prob_map_ref), geom, [up(depth_src)], [up(normal_src)],
+                      position_threshold=self.position_threshold, depth_threshold=self.depth_threshold,
+                      normal_threshold_cos=self.normal_threshold, confidence_threshold=self.confidence_threshold,
+                      min_consistent=1, per_source=True)
+        angle = r["angle_conf"][0].cpu().numpy()
+        return (r["masks"][0].cpu().numpy(), r["depth_reprojected"][0].cpu().numpy(), r["depth_src_out"][0].cpu().numpy(),
+                r["xyz_world_src"][0].cpu().numpy(), np.repeat(angle[None], 3, axis=0))

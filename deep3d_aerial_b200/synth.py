@@ -135,3 +135,58 @@ def planted_logits(num_depth, h, w, seed=0, device="cpu"):
     peak = torch.randint(0, num_depth, (1, h, w), generator=g)
     x.scatter_add_(0, peak, torch.full((1, h, w), 8.0))
     return x.to(device)
+
+
+def fusion_scene(num_src=4, height=96, width=128, seed=0, focal=None, z_mean=500.0, baseline_frac=0.04,
+                 noise=2e-3, outliers=0.1, invalid=0.03, shift=0.0, src_pad=0):
+    """Depth-map fusion inputs with the dtypes `fuse/fusion_3d_normal.py:112-133, 405-515`
+    hands `ConsistencyChecker.check`: per view a float32 depth map [H,W], camera-frame normals [H,W,3], a
+    confidence map, float32 K [3,3] and Tcw [4,4].
+
+    The scene is one tilted world plane seen by the cross rig of `make_rig`, so every view's depth is exact by
+    ray-plane intersection and views agree wherever they are not disturbed: relative depth noise `noise`
+    (threshold of the check: 1 %), a fraction `outliers` of pixels 5-30 % off, a fraction `invalid` at depth 0,
+    normals = the plane normal plus noise, confidence uniform in [0, 1].  `shift` moves the source cameras
+    sideways (in units of the image footprint) so projections leave the source maps (CuPy's wrap-around);
+    `src_pad` grows the source maps by that many pixels on every side (principal point moved along), so that
+    every projection lands inside them.
+    -> dict(ref=(depth, normal, K, E, prob), src=[(depth, normal, K, E), ...])"""
+    rng = np.random.default_rng(seed)
+    focal = float(focal) if focal else 1.6 * width
+    rig = make_rig(num_views=num_src + 1, width=width, height=height, focal=focal, z_mean=z_mean,
+                   baseline_frac=baseline_frac)
+    K = np.array([[focal, 0, (width - 1) / 2.0], [0, focal, (height - 1) / 2.0], [0, 0, 1]], dtype=np.float64)
+    n_world = np.array([0.08, -0.05, -1.0])
+    n_world /= np.linalg.norm(n_world)
+    offset = float(n_world @ np.array([0.0, 0.0, z_mean]))           # plane: n . X = offset
+    K_ref = K
+    views = []
+    for v in range(num_src + 1):
+        E = np.linalg.inv(K_ref) @ rig.proj_full[v].astype(np.float64)[:3, :4]      # [R|t]
+        pad = src_pad if v > 0 else 0
+        height, width = rig.height + 2 * pad, rig.width + 2 * pad
+        K = K_ref.copy()
+        K[0, 2] += pad
+        K[1, 2] += pad
+        ys, xs = np.mgrid[0:height, 0:width]
+        rays_cam = np.linalg.inv(K) @ np.stack([xs.ravel(), ys.ravel(), np.ones(height * width)]).astype(np.float64)
+        R, t = E[:, :3].copy(), E[:, 3].copy()
+        if v > 0 and shift:
+            t[0] += shift * rig.width * z_mean / focal
+        centre = -R.T @ t
+        dirs = R.T @ rays_cam                                        # world directions with camera z = 1
+        depth = ((offset - n_world @ centre) / (n_world @ dirs)).reshape(height, width)
+        depth = depth * (1 + noise * rng.standard_normal((height, width)))
+        bad = rng.random((height, width)) < outliers
+        depth = np.where(bad, depth * (1 + rng.uniform(0.05, 0.3, (height, width)) * rng.choice([-1, 1], (height, width))),
+                         depth)
+        depth = np.where(rng.random((height, width)) < invalid, 0.0, depth).astype(np.float32)
+        normal = (R @ n_world)[None, None, :] + 0.05 * rng.standard_normal((height, width, 3))
+        flip = rng.random((height, width)) < 0.05                    # a few normals point the other way
+        normal = np.where(flip[..., None], -normal, normal).astype(np.float32)
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = R, t
+        views.append((depth, normal, K.astype(np.float32), T.astype(np.float32)))
+    prob = rng.random((rig.height, rig.width)).astype(np.float32)
+    d, n, k, e = views[0]
+    return {"ref": (d, n, k, e, prob), "src": views[1:]}

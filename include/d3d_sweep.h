@@ -164,13 +164,69 @@ int d3d_depth_samples(const D3dSamplesArgs* args, void* cuda_stream);
 int d3d_nchw_to_nhwc(const float* in, float* out, int32_t channels, int32_t height, int32_t width,
                      void* cuda_stream);
 
+/* ---- depth-map fusion: geometric consistency check ------------------------------------
+ * Replaces ConsistencyChecker.check / check_cupy (fuse/consistency_check_n.py:29-148, ~25 CuPy launches and
+ * host round trips per source view) and the per-source accumulation loop of Fuse_Depth_Map.fuse_depths
+ * (fuse/fusion_3d_normal.py:436-530) with ONE launch per reference view over all its source views.
+ *
+ * Per reference pixel (x, y) and source view s, in the reference's own types (points fp64, normals fp32):
+ *   P = Kinv_ref (x d, y d, d);  Q = (E_s Einv_ref)[P;1];  (xs, ys) = trunc(K_s Q / z + 0.5)        (:51-72)
+ *   gather depth_src / normal_src at (ys, xs), indices wrapped modulo the map extent (CuPy's out-of-bounds rule)
+ *   back-project with the sampled depth to the world and into the reference camera                     (:76-92)
+ *   consistent = |p' - p| < position_threshold  &&  |d' - d| / d < depth_threshold  &&  prob > confidence_threshold
+ *                &&  cos(n_ref, n_src) > normal_threshold_cos  &&  d > 0                                (:95-123)
+ * The 4x4 / 3x3 matrix products and inverses are formed by the CALLER with the reference's own numpy calls, in
+ * the matrices' own dtype (fp32 in fusion_3d_normal.py:118-126), and handed over as fp64 in `geometry`:
+ *   block 0 (the reference view), 64 doubles: [0..8] Kinv_ref, [9..20] rows 0-2 of E_ref, [21..29] K_ref,
+ *                                [30..45] Einv_ref (4x4), [46..54] inverse(E_ref[:3,:3])
+ *   block 1+s (source s), 64 doubles: [0..11] rows 0-2 of E_s @ Einv_ref, [12..20] K_s, [21..29] Kinv_s,
+ *                                [30..45] Einv_s (4x4), [46..54] inverse(E_s[:3,:3])
+ * Every output pointer may be NULL (= not wanted).
+ */
+#define D3D_FUSE_MAX_SRC 16
+#define D3D_FUSE_GEOM_DOUBLES 64
+
+typedef struct D3dFuseArgs {
+    uint32_t struct_size;
+    int32_t num_src;              /* S: 1..D3D_FUSE_MAX_SRC source views                              */
+    int32_t height, width;        /* reference maps                                                   */
+    int32_t src_height, src_width;/* source maps (the reference assumes the same extent)              */
+    int32_t min_consistent;       /* final_mask = 1 + #consistent sources >= this (fusion_3d_normal.py:536) */
+    int32_t reserved0;
+    double position_threshold;    /* pixels, compared in fp64                                         */
+    float depth_threshold;        /* relative, compared in fp32                                       */
+    float confidence_threshold;   /* on prob_ref, fp32                                                */
+    float normal_threshold_cos;   /* cos(normal_threshold degrees), fp32                              */
+    int32_t reserved1;
+    const float* depth_ref;       /* [H,W]                                                            */
+    const float* normal_ref;      /* [H,W,3] camera-frame normals                                     */
+    const float* prob_ref;        /* [H,W] photometric confidence                                     */
+    const double* geometry;       /* [(1+S) * D3D_FUSE_GEOM_DOUBLES], see above                       */
+    const float* depth_src[D3D_FUSE_MAX_SRC];   /* S x [Hs,Ws]                                        */
+    const float* normal_src[D3D_FUSE_MAX_SRC];  /* S x [Hs,Ws,3]                                      */
+    float* depth_src_out[D3D_FUSE_MAX_SRC];     /* S x [Hs,Ws]: depth_src with the pixels consumed by this
+                                     reference view set to 0 (:128-131); the library copies depth_src[s]
+                                     into it first.  Must not alias depth_src[s]                      */
+    uint8_t* mask;                /* [S,H,W] consistency mask per source                              */
+    float* depth_reprojected;     /* [S,H,W] d' where consistent, else 0                              */
+    float* xyz_world_src;         /* [S,3,H,W] world point of the source sample where consistent, else 0 */
+    float* angle_conf;            /* [S,H,W] max(cos, 0) where consistent, else 0 (one plane; the reference
+                                     repeats it three times, :112)                                    */
+    int32_t* consistent_count;    /* [H,W] geo_mask_sum = 1 + sum_s mask_s                            */
+    float* xyz_fused;             /* [3,H,W] (xyz_ref + sum_s conf_s xyz_s) / (1 + sum_s conf_s)      */
+    uint8_t* final_mask;          /* [H,W]                                                            */
+    float* depth_ref_filtered;    /* [H,W] depth_ref where final_mask, else 0 (fusion_3d_normal.py:541) */
+} D3dFuseArgs;
+
+int d3d_consistency_fuse(const D3dFuseArgs* args, void* cuda_stream);
+
 /* Thread-local description of the last error returned on this thread ("" if none). */
 const char* d3d_last_error(void);
 int d3d_version(void);
 /* Number of kernels this library has launched in the calling process (bench accounting). */
 int64_t d3d_launch_count(void);
 /* sizeof() of an argument struct as compiled into the library: 0 = D3dCostVolumeArgs,
- * 1 = D3dRegressArgs, 2 = D3dSamplesArgs; -1 for anything else.  Lets a binding check its layout
+ * 1 = D3dRegressArgs, 2 = D3dSamplesArgs, 3 = D3dFuseArgs; -1 for anything else.  Lets a binding check its layout
  * without a GPU. */
 int32_t d3d_abi_sizeof(int32_t which);
 

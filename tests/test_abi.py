@@ -37,7 +37,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_struct_layouts_match(lib):
-    for which, struct in enumerate((_lib.CostVolumeArgs, _lib.RegressArgs, _lib.SamplesArgs)):
+    for which, struct in enumerate((_lib.CostVolumeArgs, _lib.RegressArgs, _lib.SamplesArgs, _lib.FuseArgs)):
         assert lib.d3d_abi_sizeof(which) == C.sizeof(struct)
     assert lib.d3d_abi_sizeof(99) == -1
     assert lib.d3d_version() == 100
