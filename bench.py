@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -43,7 +44,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg3"],
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg3", "fuse"],
                     help="cfg2 = the configuration the metric is quoted on; cfg3 = the AdaMVS 3-stage cascade")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (A/B; 0 = production)")
@@ -570,14 +571,140 @@ def run_cascade(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------ row f3
+def run_fuse(args):
+    """the depth-map fusion consistency check of one reference view against its 10 source
+    views (fuse/fusion_3d_normal.py --fusion_num) at the full 1856 x 2752 depth-map size, one
+    `d3d_consistency_fuse` launch per step.  `value`: pixel pairs (reference pixel x source view) per second with
+    every map resident in HBM; `e2e`: the same from pinned host maps (reference maps + geometry up, count / fused
+    points / final mask / filtered depth down; the source maps stay resident, as they do across the reference
+    views of a scene block); cpu_baseline: the numpy oracle (= the reference's CuPy code on numpy) on a row band."""
+    import numpy as np
+    import torch
+
+    from deep3d_aerial_b200 import _lib, fusion, shard, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the fusion kernel has no CPU path")
+    _lib.load()
+    torch.set_grad_enabled(False)
+    rank, world, local = shard.init()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    S, H, W = 10, 2752, 1856
+    sc = synth.fusion_scene(num_src=S, height=H, width=W, seed=11 + rank, focal=4000.0)
+    d, n, k, e, prob = sc["ref"]
+    th = dict(position_threshold=1.0, depth_threshold=0.01, normal_threshold_cos=math.cos(math.radians(10.0)),
+              confidence_threshold=0.2, min_consistent=4)
+    geom_host = fusion.pair_geometry(k, e, [v[2] for v in sc["src"]], [v[3] for v in sc["src"]])
+    up = lambda x: torch.from_numpy(x).to(dev)                                   # noqa: E731
+    ref_dev = (up(d), up(n), up(prob))
+    geom = up(geom_host)
+    src_d, src_n = [up(v[0]) for v in sc["src"]], [up(v[1]) for v in sc["src"]]
+    out = fusion.fuse_view(*ref_dev, geom, src_d, src_n, **th)
+    pairs = H * W * S
+    # algorithmic bytes per step: reference maps read once (depth 4 + normal 12 + prob 4), per source view the
+    # gathered depth + normal (16) and the mask (1), the copy of every source map (4 + 4), and the fused outputs
+    # (count 4 + point 12 + final mask 1 + filtered depth 4)
+    alg_bytes = H * W * (20 + S * (16 + 1 + 8) + 21)
+
+    def step():
+        fusion.fuse_view(*ref_dev, geom, src_d, src_n, out=out, **th)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    shard.barrier()
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step()
+    t1.record()
+    torch.cuda.synchronize()
+    shard.barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop()
+    ms_total = shard.join_max(t0.elapsed_time(t1))
+    ms_step = ms_total / args.steps
+    value = shard.join_sum(pairs * args.steps) / (ms_total * 1e-3) / 1e9
+
+    e2e = None
+    if not args.no_e2e:
+        pin = [torch.from_numpy(x).pin_memory() for x in (d, n, prob, geom_host)]
+        host_out = {key: torch.empty(out[key].shape, dtype=out[key].dtype).pin_memory()
+                    for key in ("count", "xyz", "final_mask", "depth_ref_filtered")}
+        stage = [torch.empty_like(t, device=dev) for t in pin]
+
+        def e2e_step():
+            for dst, src in zip(stage, pin):
+                dst.copy_(src, non_blocking=True)
+            fusion.fuse_view(stage[0], stage[1], stage[2], stage[3], src_d, src_n, out=out, **th)
+            for key, dst in host_out.items():
+                dst.copy_(out[key], non_blocking=True)
+
+        for _ in range(3):
+            e2e_step()
+        shard.barrier()
+        torch.cuda.synchronize()
+        t0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        t1.record()
+        torch.cuda.synchronize()
+        shard.barrier()
+        ms_e2e = shard.join_max(t0.elapsed_time(t1))
+        e2e = {"value": shard.join_sum(pairs * args.steps) / (ms_e2e * 1e-3) / 1e9, "unit": "Gpixel-pair/s",
+               "ms_per_step": ms_e2e / args.steps,
+               "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in pin),
+               "d2h_bytes_per_step": sum(t.numel() * t.element_size() for t in host_out.values())}
+    total_launches = int(shard.join_sum(launches))
+    if rank != 0:
+        return 0
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import fuse_np
+        rows = 256
+        kw = dict(position_threshold=1.0, depth_threshold=0.01, normal_cos=th["normal_threshold_cos"], confidence_threshold=0.2)
+        t = time.perf_counter()
+        fuse_np.fuse_view(d[:rows], n[:rows], k, e, prob[:rows], sc["src"], min_consistent=4, **kw)
+        dt = time.perf_counter() - t
+        cpu = {"value": rows * W * S / dt / 1e9, "unit": "Gpixel-pair/s", "cores": 1, "kind": "port",
+               "sample": "the first %d of %d rows of the reference view against all %d source views, numpy %s"
+                         % (rows, H, S, np.__version__)}
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    line = {
+        "metric": "consistency-checked pixel pairs/s", "value": value, "unit": "Gpixel-pair/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "depth-map fusion consistency check, 1 reference view x %d source views at %dx%d "
+                               "(fuse/consistency_check_n.py)" % (S, W, H),
+                   "l2": "maps of one step (1.3 GB) exceed the 126 MB L2", "views_per_step_per_gpu": 1,
+                   "final_mask_fraction": float(out["final_mask"].float().mean())},
+        "ref_views_per_s": world * 1e3 / ms_step,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "consistency_fuse_kernel", "algorithmic_bytes": alg_bytes,
+                     "peak_source": peak_src},
+        "clocks": clocks, "gpu_launches": total_launches, "e2e": e2e, "cpu_baseline": cpu,
+        "note": "row f3 of SURVEY.md 8f; the headline line is --workload cfg2",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     args = parse()
     if args.impl == "reference":
-        if args.workload == "cfg3":
+        if args.workload in ("cfg3", "fuse"):
             args.workload = "cfg2"     # the reference arm is quoted on the headline configuration
         return run_reference(args)
     if args.workload == "cfg3":
         return run_cascade(args)
+    if args.workload == "fuse":
+        return run_fuse(args)
     return run_ours(args)
 
 

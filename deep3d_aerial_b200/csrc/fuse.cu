@@ -7,6 +7,8 @@
 // gathers of a warp fall into a handful of 128-byte lines.  Points are fp64 and normals fp32 -- the types the
 // reference's own promotion rules produce (int64 grid x fp32 depth -> fp64; fp32 rotation x fp32 normal -> fp32).
 // Bound: HBM (20 B per reference pixel + 16 B gathered and <= 33 B written per pixel and source view).
+#include <cmath>
+
 #include "common.cuh"
 
 namespace d3d {
@@ -30,25 +32,39 @@ struct FuseParams {
     float* __restrict__ xyz_fused;
     uint8_t* __restrict__ final_mask;
     float* __restrict__ depth_ref_filtered;
-    double position_threshold;
+    double dist2_limit;               // see dist2_limit_of
     float depth_threshold, confidence_threshold, normal_threshold_cos;
     int S, H, W, Hs, Ws, min_consistent;
 };
 
-// row-major 3x3 times a 3-vector / 3 rows of a 4x4 times [v;w]
-__device__ __forceinline__ void mat3(const double* m, double a, double b, double c, double& x, double& y, double& z) {
-    x = m[0] * a + m[1] * b + m[2] * c;
-    y = m[3] * a + m[4] * b + m[5] * c;
-    z = m[6] * a + m[7] * b + m[8] * c;
+// Geometry block (D3D_FUSE_GEOM_DOUBLES = 64 doubles; rows padded to 4 so every row is two 16-byte loads):
+//   [0..11] A 3x4   [12..23] B 3x4   [24..35] C 3x4   [36..51] D 4x4   [52..63] R 3x4 (staged as fp32)
+constexpr int kA = 0, kB = 12, kC = 24, kD = 36, kR = 52;
+
+__device__ __forceinline__ double row3(const double* r, double a, double b, double c) {
+    const double2 u = *reinterpret_cast<const double2*>(r), v = *reinterpret_cast<const double2*>(r + 2);
+    return u.x * a + u.y * b + v.x * c;                    // fma(c2, c, fma(c1, b, c0 * a)): dgemm's order
 }
 __device__ __forceinline__ double row4(const double* r, double a, double b, double c, double w) {
-    return r[0] * a + r[1] * b + r[2] * c + r[3] * w;
+    const double2 u = *reinterpret_cast<const double2*>(r), v = *reinterpret_cast<const double2*>(r + 2);
+    return u.x * a + u.y * b + v.x * c + v.y * w;
 }
 // fp32 rotation of an fp32 normal (np.matmul of two float32 arrays stays float32)
-__device__ __forceinline__ void rot3f(const double* m, float a, float b, float c, float& x, float& y, float& z) {
-    x = (float)m[0] * a + (float)m[1] * b + (float)m[2] * c;
-    y = (float)m[3] * a + (float)m[4] * b + (float)m[5] * c;
-    z = (float)m[6] * a + (float)m[7] * b + (float)m[8] * c;
+__device__ __forceinline__ void rot3f(const float* m, float a, float b, float c, float& x, float& y, float& z) {
+    const float4 r0 = *reinterpret_cast<const float4*>(m), r1 = *reinterpret_cast<const float4*>(m + 4),
+                 r2 = *reinterpret_cast<const float4*>(m + 8);
+    x = r0.x * a + r0.y * b + r0.z * c;
+    y = r1.x * a + r1.y * b + r1.z * c;
+    z = r2.x * a + r2.y * b + r2.z * c;
+}
+// a1/b and a2/b, correctly rounded, from ONE reciprocal: q0 = a*r is within an ulp of a/b and the residual
+// correction fma(fma(-b, q0, a), r, q0) rounds it correctly (Markstein), as the tail of IEEE division does
+__device__ __forceinline__ void div_pair(double a1, double a2, double b, double& q1, double& q2) {
+    const double r = __drcp_rn(b);
+    double t = a1 * r;
+    q1 = fma(fma(-b, t, a1), r, t);
+    t = a2 * r;
+    q2 = fma(fma(-b, t, a2), r, t);
 }
 // Python-style modulo: CuPy wraps out-of-bounds integer-array indices around the axis
 __device__ __forceinline__ long long wrap(long long i, int n) {
@@ -57,8 +73,14 @@ __device__ __forceinline__ long long wrap(long long i, int n) {
 }
 
 __global__ void __launch_bounds__(kFuseThreads) consistency_fuse_kernel(const FuseParams p) {
-    extern __shared__ double geo[];                        // (1 + S) blocks of kGeom doubles
-    for (int i = threadIdx.x; i < (1 + p.S) * kGeom; i += kFuseThreads) geo[i] = __ldg(p.geometry + i);
+    extern __shared__ double geo[];                        // (1 + S) blocks of kGeom doubles, then the fp32 rotations
+    float* rotf = reinterpret_cast<float*>(geo + (1 + p.S) * kGeom);
+    for (int i = threadIdx.x; i < (1 + p.S) * kGeom; i += kFuseThreads) {
+        const double v = __ldg(p.geometry + i);
+        geo[i] = v;
+        const int blk = i / kGeom, k = i % kGeom;
+        if (k >= kR) rotf[blk * 12 + (k - kR)] = (float)v;
+    }
     __syncthreads();
 
     const long long hw = (long long)p.H * p.W;
@@ -70,12 +92,13 @@ __global__ void __launch_bounds__(kFuseThreads) consistency_fuse_kernel(const Fu
     const float prob = __ldg(p.prob_ref + pix);
     const float n0 = __ldg(p.normal_ref + 3 * pix), n1 = __ldg(p.normal_ref + 3 * pix + 1),
                 n2 = __ldg(p.normal_ref + 3 * pix + 2);
-    const double dd = (double)d;
+    const double dd = (double)d, xd = (double)x, yd = (double)y;
     const double* G0 = geo;
-    double px, py, pz;                                     // reference camera space (:51-53)
-    mat3(G0, (double)x * dd, (double)y * dd, dd, px, py, pz);
+    // reference camera space (:51-53): Kinv_ref (x d, y d, d)
+    const double vx = xd * dd, vy = yd * dd;
+    const double px = row3(G0 + kA, vx, vy, dd), py = row3(G0 + kA + 4, vx, vy, dd), pz = row3(G0 + kA + 8, vx, vy, dd);
     float nrx, nry, nrz;                                   // reference normal in the world (:104-106)
-    rot3f(G0 + 46, n0, n1, n2, nrx, nry, nrz);
+    rot3f(rotf, n0, n1, n2, nrx, nry, nrz);
     // numpy rounds every product before it adds (np.sum(a*b), np.linalg.norm): no FMA contraction on these
     auto dot3 = [](float a0, float a1, float a2, float b0, float b1, float b2) {
         return __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
@@ -83,8 +106,8 @@ __global__ void __launch_bounds__(kFuseThreads) consistency_fuse_kernel(const Fu
     const float nr_norm = sqrtf(dot3(nrx, nry, nrz, nrx, nry, nrz));
 
     // accumulators of fusion_3d_normal.py:449-455, 525-527: world point of the reference pixel, confidence 1
-    float ax = (float)row4(G0 + 30, px, py, pz, 1.0), ay = (float)row4(G0 + 34, px, py, pz, 1.0),
-          az = (float)row4(G0 + 38, px, py, pz, 1.0);
+    float ax = (float)row4(G0 + kD, px, py, pz, 1.0), ay = (float)row4(G0 + kD + 4, px, py, pz, 1.0),
+          az = (float)row4(G0 + kD + 8, px, py, pz, 1.0);
     float aconf = 1.f;
     int count = 1;
     const bool gate = prob > p.confidence_threshold && d > 0.f;
@@ -92,35 +115,54 @@ __global__ void __launch_bounds__(kFuseThreads) consistency_fuse_kernel(const Fu
     for (int s = 0; s < p.S; ++s) {
         const double* G = geo + (1 + s) * kGeom;
         // source camera space and pixel (:56-72)
-        const double qx = row4(G, px, py, pz, 1.0), qy = row4(G + 4, px, py, pz, 1.0), qz = row4(G + 8, px, py, pz, 1.0);
-        double kx, ky, kz;
-        mat3(G + 12, qx, qy, qz, kx, ky, kz);
-        const long long xs = __double2ll_rz(kx / kz + 0.5), ys = __double2ll_rz(ky / kz + 0.5);
-        const long long at = wrap(ys, p.Hs) * p.Ws + wrap(xs, p.Ws);
+        const double qx = row4(G + kA, px, py, pz, 1.0), qy = row4(G + kA + 4, px, py, pz, 1.0),
+                     qz = row4(G + kA + 8, px, py, pz, 1.0);
+        const double kx = row3(G + kB, qx, qy, qz), ky = row3(G + kB + 4, qx, qy, qz), kz = row3(G + kB + 8, qx, qy, qz);
+        double fxs, fys;
+        div_pair(kx, ky, kz, fxs, fys);
+        fxs += 0.5;
+        fys += 0.5;
+        long long at;
+        double xsd, ysd;
+        if (fabs(fxs) < 2147483000.0 && fabs(fys) < 2147483000.0) {      // (NaN fails the test)
+            int xi = __double2int_rz(fxs), yi = __double2int_rz(fys);
+            xsd = (double)xi;
+            ysd = (double)yi;
+            if ((unsigned)xi >= (unsigned)p.Ws) { xi %= p.Ws; if (xi < 0) xi += p.Ws; }    // CuPy's wrap-around
+            if ((unsigned)yi >= (unsigned)p.Hs) { yi %= p.Hs; if (yi < 0) yi += p.Hs; }
+            at = (long long)yi * p.Ws + xi;
+        } else {                                                         // astype(int) is int64 upstream
+            const long long xs = __double2ll_rz(fxs), ys = __double2ll_rz(fys);
+            xsd = (double)xs;
+            ysd = (double)ys;
+            at = wrap(ys, p.Hs) * p.Ws + wrap(xs, p.Ws);
+        }
         const float sd = __ldg(p.depth_src[s] + at);
         const float* np_ = p.normal_src[s] + 3 * at;
         const float m0 = __ldg(np_), m1 = __ldg(np_ + 1), m2 = __ldg(np_ + 2);
         // back to the source camera, the world, the reference camera (:76-92)
         const double sdd = (double)sd;
-        double cx, cy, cz;
-        mat3(G + 21, (double)xs * sdd, (double)ys * sdd, sdd, cx, cy, cz);
-        const double wx = row4(G + 30, cx, cy, cz, 1.0), wy = row4(G + 34, cx, cy, cz, 1.0),
-                     wz = row4(G + 38, cx, cy, cz, 1.0), ww = row4(G + 42, cx, cy, cz, 1.0);
-        const double rx = row4(G0 + 9, wx, wy, wz, ww), ry = row4(G0 + 13, wx, wy, wz, ww),
-                     rz = row4(G0 + 17, wx, wy, wz, ww);
+        const double bx = xsd * sdd, by = ysd * sdd;
+        const double cx = row3(G + kC, bx, by, sdd), cy = row3(G + kC + 4, bx, by, sdd), cz = row3(G + kC + 8, bx, by, sdd);
+        const double wx = row4(G + kD, cx, cy, cz, 1.0), wy = row4(G + kD + 4, cx, cy, cz, 1.0),
+                     wz = row4(G + kD + 8, cx, cy, cz, 1.0), ww = row4(G + kD + 12, cx, cy, cz, 1.0);
+        const double rx = row4(G0 + kB, wx, wy, wz, ww), ry = row4(G0 + kB + 4, wx, wy, wz, ww),
+                     rz = row4(G0 + kB + 8, wx, wy, wz, ww);
         const float depth_rep = (float)rz;
-        double ux, uy, uz;
-        mat3(G0 + 21, rx, ry, rz, ux, uy, uz);
-        const float xr = (float)(ux / uz), yr = (float)(uy / uz);
-        // position (fp32 pixel minus int64 grid -> fp64), depth (fp32), normal (fp32) tests (:95-123)
-        const double ex = (double)xr - (double)x, ey = (double)yr - (double)y;
-        const double dist = sqrt(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)));
+        const double ux = row3(G0 + kC, rx, ry, rz), uy = row3(G0 + kC + 4, rx, ry, rz), uz = row3(G0 + kC + 8, rx, ry, rz);
+        double xrd, yrd;
+        div_pair(ux, uy, uz, xrd, yrd);
+        const float xr = (float)xrd, yr = (float)yrd;
+        // position (fp32 pixel minus int64 grid -> fp64; sqrt(s) < t restated as s < dist2_limit, exactly: abi),
+        // depth (fp32), normal (fp32) tests (:95-123)
+        const double ex = (double)xr - xd, ey = (double)yr - yd;
+        const double dist2 = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
         const float rel = __fdiv_rn(fabsf(depth_rep - d), d);
         float nsx, nsy, nsz;
-        rot3f(G + 46, m0, m1, m2, nsx, nsy, nsz);
+        rot3f(rotf + (1 + s) * 12, m0, m1, m2, nsx, nsy, nsz);
         const float cosv = __fdiv_rn(dot3(nrx, nry, nrz, nsx, nsy, nsz),
                                      __fmul_rn(nr_norm, sqrtf(dot3(nsx, nsy, nsz, nsx, nsy, nsz))));
-        const bool ok = gate && dist < p.position_threshold && rel < p.depth_threshold && cosv > p.normal_threshold_cos;
+        const bool ok = gate && dist2 < p.dist2_limit && rel < p.depth_threshold && cosv > p.normal_threshold_cos;
 
         const float conf = ok ? fmaxf(cosv, 0.f) : 0.f;
         const float fx = ok ? (float)wx : 0.f, fy = ok ? (float)wy : 0.f, fz = ok ? (float)wz : 0.f;
@@ -150,6 +192,17 @@ __global__ void __launch_bounds__(kFuseThreads) consistency_fuse_kernel(const Fu
         p.xyz_fused[hw + pix] = __fdiv_rn(ay, aconf);
         p.xyz_fused[2 * hw + pix] = __fdiv_rn(az, aconf);
     }
+}
+
+// smallest s with sqrt(s) >= t: `sqrt(s) < t` (consistency_check_n.py:95, 116) is then exactly `s < limit`
+// (IEEE sqrt is correctly rounded and monotonic, on the host as on the device)
+static double dist2_limit_of(double t) {
+    if (!(t > 0.0)) return 0.0;                            // nothing is closer than a non-positive threshold
+    if (std::isinf(t)) return t;
+    double s = t * t;
+    while (s > 0.0 && std::sqrt(s) >= t) s = std::nextafter(s, 0.0);
+    while (std::sqrt(std::nextafter(s, INFINITY)) < t) s = std::nextafter(s, INFINITY);
+    return std::sqrt(s) < t ? std::nextafter(s, INFINITY) : s;
 }
 
 }  // namespace d3d
@@ -194,14 +247,14 @@ extern "C" int d3d_consistency_fuse(const D3dFuseArgs* a, void* cuda_stream) {
     p.mask = a->mask; p.depth_reprojected = a->depth_reprojected; p.xyz_world_src = a->xyz_world_src;
     p.angle_conf = a->angle_conf; p.consistent_count = a->consistent_count; p.xyz_fused = a->xyz_fused;
     p.final_mask = a->final_mask; p.depth_ref_filtered = a->depth_ref_filtered;
-    p.position_threshold = a->position_threshold;
+    p.dist2_limit = dist2_limit_of(a->position_threshold);
     p.depth_threshold = a->depth_threshold; p.confidence_threshold = a->confidence_threshold;
     p.normal_threshold_cos = a->normal_threshold_cos;
     p.S = a->num_src; p.H = a->height; p.W = a->width; p.Hs = a->src_height; p.Ws = a->src_width;
     p.min_consistent = a->min_consistent;
 
     const unsigned blocks = (unsigned)((hw + kFuseThreads - 1) / kFuseThreads);
-    const size_t smem = (size_t)(1 + a->num_src) * kGeom * sizeof(double);
+    const size_t smem = (size_t)(1 + a->num_src) * (kGeom * sizeof(double) + 12 * sizeof(float));
     consistency_fuse_kernel<<<blocks, kFuseThreads, smem, stream>>>(p);
     count_launch();
     return check_launch("consistency_fuse_kernel");

@@ -31,20 +31,26 @@ def pair_geometry(intrinsics_ref, extrinsics_ref, intrinsics_src: Sequence, extr
     computed as the reference computes it (consistency_check_n.py:52, 56, 76, 80, 103, 107;
     fusion_3d_normal.py:449-451)."""
     k_ref, e_ref = np.asarray(intrinsics_ref), np.asarray(extrinsics_ref)
-    g = np.zeros((1 + len(intrinsics_src), _lib.FUSE_GEOM_DOUBLES), dtype=np.float64)
+    g = np.zeros((1 + len(intrinsics_src), 64), dtype=np.float64)
+
+    def put(block, at, m):                                   # row-major, rows padded to 4 entries
+        m = np.asarray(m)
+        view = g[block, at:at + 4 * m.shape[0]].reshape(m.shape[0], 4)
+        view[:, :m.shape[1]] = m
+
     e_ref_inv = np.linalg.inv(e_ref)
-    g[0, 0:9] = np.linalg.inv(k_ref).reshape(-1)
-    g[0, 9:21] = e_ref[:3, :4].reshape(-1)
-    g[0, 21:30] = k_ref.reshape(-1)
-    g[0, 30:46] = e_ref_inv.reshape(-1)
-    g[0, 46:55] = np.linalg.inv(e_ref[:3, :3]).reshape(-1)
+    put(0, 0, np.linalg.inv(k_ref))
+    put(0, 12, e_ref[:3, :4])
+    put(0, 24, k_ref)
+    put(0, 36, e_ref_inv)
+    put(0, 52, np.linalg.inv(e_ref[:3, :3]))
     for s, (k, e) in enumerate(zip(intrinsics_src, extrinsics_src)):
         k, e = np.asarray(k), np.asarray(e)
-        g[1 + s, 0:12] = np.matmul(e, e_ref_inv)[:3, :4].reshape(-1)
-        g[1 + s, 12:21] = k.reshape(-1)
-        g[1 + s, 21:30] = np.linalg.inv(k).reshape(-1)
-        g[1 + s, 30:46] = np.linalg.inv(e).reshape(-1)
-        g[1 + s, 46:55] = np.linalg.inv(e[:3, :3]).reshape(-1)
+        put(1 + s, 0, np.matmul(e, e_ref_inv)[:3, :4])
+        put(1 + s, 12, k)
+        put(1 + s, 24, np.linalg.inv(k))
+        put(1 + s, 36, np.linalg.inv(e))
+        put(1 + s, 52, np.linalg.inv(e[:3, :3]))
     return g
 
 

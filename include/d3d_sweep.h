@@ -177,10 +177,12 @@ int d3d_nchw_to_nhwc(const float* in, float* out, int32_t channels, int32_t heig
  *                &&  cos(n_ref, n_src) > normal_threshold_cos  &&  d > 0                                (:95-123)
  * The 4x4 / 3x3 matrix products and inverses are formed by the CALLER with the reference's own numpy calls, in
  * the matrices' own dtype (fp32 in fusion_3d_normal.py:118-126), and handed over as fp64 in `geometry`:
- *   block 0 (the reference view), 64 doubles: [0..8] Kinv_ref, [9..20] rows 0-2 of E_ref, [21..29] K_ref,
- *                                [30..45] Einv_ref (4x4), [46..54] inverse(E_ref[:3,:3])
- *   block 1+s (source s), 64 doubles: [0..11] rows 0-2 of E_s @ Einv_ref, [12..20] K_s, [21..29] Kinv_s,
- *                                [30..45] Einv_s (4x4), [46..54] inverse(E_s[:3,:3])
+ * one block of 64 doubles per view, matrices row-major with every row padded to 4 entries (3x3 -> 3x4, pad 0):
+ *   doubles [0..11] A 3x4, [12..23] B 3x4, [24..35] C 3x4, [36..51] D 4x4, [52..63] R 3x4
+ *   block 0 (the reference view):  A = Kinv_ref, B = rows 0-2 of E_ref, C = K_ref, D = Einv_ref,
+ *                                  R = inverse(E_ref[:3,:3])
+ *   block 1+s (source view s):     A = rows 0-2 of E_s @ Einv_ref, B = K_s, C = Kinv_s, D = Einv_s,
+ *                                  R = inverse(E_s[:3,:3])
  * Every output pointer may be NULL (= not wanted).
  */
 #define D3D_FUSE_MAX_SRC 16

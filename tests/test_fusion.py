@@ -64,10 +64,12 @@ def test_pair_geometry_layout():
     _, _, k, e, _ = sc["ref"]
     g = fusion.pair_geometry(k, e, [v[2] for v in sc["src"]], [v[3] for v in sc["src"]])
     assert g.shape == (3, 64) and g.dtype == np.float64
-    assert np.array_equal(g[0, 21:30], k.reshape(-1).astype(np.float64))
-    assert np.array_equal(g[0, 30:46], np.linalg.inv(e).reshape(-1).astype(np.float64))        # float32 inverse, widened
-    assert np.array_equal(g[2, 0:12], np.matmul(sc["src"][1][3], np.linalg.inv(e))[:3].reshape(-1).astype(np.float64))
-    assert (g[:, 55:] == 0).all()
+    pad = lambda m: np.pad(np.asarray(m, dtype=np.float64), ((0, 0), (0, 4 - m.shape[1]))).reshape(-1)   # noqa: E731
+    assert np.array_equal(g[0, 24:36], pad(k))
+    assert np.array_equal(g[0, 36:52], pad(np.linalg.inv(e)))                                  # float32 inverse, widened
+    assert np.array_equal(g[2, 0:12], pad(np.matmul(sc["src"][1][3], np.linalg.inv(e))[:3]))
+    assert np.array_equal(g[1, 52:64], pad(np.linalg.inv(sc["src"][0][3][:3, :3])))
+    assert (g[0, 3:12:4] == 0).all() and (g[:, 27:36:4] == 0).all()       # the padding of the 3x3 matrices
 
 
 def test_fuse_validation_needs_no_gpu():
