@@ -72,6 +72,10 @@ __device__ __forceinline__ long long wrap(long long i, int n) {
     return r < 0 ? r + n : r;
 }
 
+// kPerSource: the per-source maps of ConsistencyChecker.check are wanted (depth_reprojected, xyz_world_src,
+// angle_conf); kFused: the accumulated outputs of fuse_depths are wanted.  Compile-time so the common fused call
+// carries no dead stores or pointer tests in its loop (the kernel is issue-bound).
+template <bool kPerSource, bool kFused>
 __global__ void __launch_bounds__(kFuseThreads) consistency_fuse_kernel(const FuseParams p) {
     extern __shared__ double geo[];                        // (1 + S) blocks of kGeom doubles, then the fp32 rotations
     float* rotf = reinterpret_cast<float*>(geo + (1 + p.S) * kGeom);
@@ -176,13 +180,16 @@ __global__ void __launch_bounds__(kFuseThreads) consistency_fuse_kernel(const Fu
         }
         const long long o = (long long)s * hw + pix;
         if (p.mask) p.mask[o] = ok;
-        if (p.depth_reprojected) p.depth_reprojected[o] = ok ? depth_rep : 0.f;
-        if (p.angle_conf) p.angle_conf[o] = conf;
-        if (p.xyz_world_src) {
-            float* q = p.xyz_world_src + (long long)s * 3 * hw + pix;
-            q[0] = fx; q[hw] = fy; q[2 * hw] = fz;
+        if (kPerSource) {
+            if (p.depth_reprojected) p.depth_reprojected[o] = ok ? depth_rep : 0.f;
+            if (p.angle_conf) p.angle_conf[o] = conf;
+            if (p.xyz_world_src) {
+                float* q = p.xyz_world_src + (long long)s * 3 * hw + pix;
+                q[0] = fx; q[hw] = fy; q[2 * hw] = fz;
+            }
         }
     }
+    if (!kFused) return;
     const bool keep = count >= p.min_consistent;
     if (p.consistent_count) p.consistent_count[pix] = count;
     if (p.final_mask) p.final_mask[pix] = keep;
@@ -255,7 +262,11 @@ extern "C" int d3d_consistency_fuse(const D3dFuseArgs* a, void* cuda_stream) {
 
     const unsigned blocks = (unsigned)((hw + kFuseThreads - 1) / kFuseThreads);
     const size_t smem = (size_t)(1 + a->num_src) * (kGeom * sizeof(double) + 12 * sizeof(float));
-    consistency_fuse_kernel<<<blocks, kFuseThreads, smem, stream>>>(p);
+    const bool per_source = p.depth_reprojected || p.angle_conf || p.xyz_world_src;
+    const bool fused = p.consistent_count || p.final_mask || p.depth_ref_filtered || p.xyz_fused;
+    if (per_source && fused) consistency_fuse_kernel<true, true><<<blocks, kFuseThreads, smem, stream>>>(p);
+    else if (per_source) consistency_fuse_kernel<true, false><<<blocks, kFuseThreads, smem, stream>>>(p);
+    else consistency_fuse_kernel<false, true><<<blocks, kFuseThreads, smem, stream>>>(p);
     count_launch();
     return check_launch("consistency_fuse_kernel");
 }

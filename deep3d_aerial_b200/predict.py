@@ -47,6 +47,11 @@ def build_parser():
     p.add_argument("--reference_root", default=os.environ.get("DEEP3D_REFERENCE_ROOT", ""),
                    help="the reference checkout's mvs/mvs_cas directory (its `models` package holds the networks)")
     p.add_argument("--plane_loop_graphs", action="store_true", help="CUDA-graph the per-plane loops (row f1)")
+    p.add_argument("--feature_cache", type=int, default=0,
+                   help="keep the FeatureNet pyramids of this many images resident and reuse them across reference "
+                        "views (row f4); 0 = recompute per view, as upstream")
+    p.add_argument("--partition", default="round_robin", choices=["round_robin", "contiguous"],
+                   help="how reference views are dealt to ranks; contiguous keeps neighbours (shared sources) together")
     return p
 
 
@@ -84,7 +89,10 @@ def predict_depth(args, model=None):
     import numpy as np
     import torch
 
+    import contextlib
+
     from . import dataset, depthnets, shard
+    from .feature_cache import FeatureCache
 
     if str(args.display).lower() in ("false", "0", "no"):
         args.display = False
@@ -99,17 +107,22 @@ def predict_depth(args, model=None):
     if args.plane_loop_graphs:
         depthnets.PLANE_LOOP_GRAPHS = True
     model = model.to(device).eval()
+    cache = None
+    if args.feature_cache > 0 and hasattr(model, "feature"):
+        cache = FeatureCache(args.feature_cache).attach(model.feature)
     views = dataset.MVSDataset(args.data_folder, "val", args.view_num, args.normalize, args)
     os.makedirs(args.output_folder, exist_ok=True)
     written = []
     t_first = time.time()
     with torch.no_grad():
-        for idx in shard.partition(range(len(views)), world, rank):
+        for idx in shard.partition(range(len(views)), world, rank, mode=args.partition):
             t0 = time.time()
             sample = dataset.collate(views[idx])
             imgs = sample["imgs"].to(device, non_blocking=True)
             proj = {k: v.to(device) for k, v in sample["proj_matrices"].items()}
-            outputs = model(imgs, proj, sample["depth_values"].to(device))
+            ids = views.sample_list[idx][:args.view_num]
+            with (cache.views(ids) if cache else contextlib.nullcontext()):
+                outputs = model(imgs, proj, sample["depth_values"].to(device))
             depth = outputs["depth"].float().cpu().numpy()
             prob = outputs["photometric_confidence"].float().cpu().numpy()
             t1 = time.time()
@@ -121,6 +134,9 @@ def predict_depth(args, model=None):
             print("depth inference {} finished, image {} finished, ({:3f}s and {:3f} sec/step)".format(
                 len(written), os.path.splitext(location[3])[0], t1 - t0, time.time() - t1))
     print("final, total_cnt = {}, total_time = {:3f}".format(len(written), time.time() - t_first))
+    if cache:
+        print("feature cache:", cache.stats())
+        cache.detach()
     return written
 
 
