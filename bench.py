@@ -441,7 +441,7 @@ def run_cascade(args):
     import torch
     import torch.nn.functional as F
 
-    from deep3d_aerial_b200 import _lib, shard, sweep, synth
+    from deep3d_aerial_b200 import _lib, depthnets, shard, sweep, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the sweep engine has no CPU path")
@@ -450,6 +450,7 @@ def run_cascade(args):
     rank, world, local = shard.init()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    batch_planes = int(os.environ.get("D3D_STREAM_BATCH_PLANES", depthnets.STREAM_BATCH_PLANES))
     v, full_h, full_w, num_depth = 5, 2752, 1856, 384
     rig = synth.make_rig(num_views=v)
     base_interval = (rig.dmax - rig.dmin) / num_depth
@@ -503,9 +504,13 @@ def run_cascade(args):
                                     plane_major=True)
             mark("s%d_regress" % (i + 1))
             r = None
-            for k in range(s["d"]):            # plane at a time, as the GRU regulariser delivers it
-                r = sweep.depth_regress(s["logits"][k:k + 1], hyps, softmax_mode=sweep.SOFTMAX_RAW_EXP, d_begin=k,
-                                        num_depth=s["d"], state=s["state"], finalize=(k == s["d"] - 1))
+            held = []                          # planes arrive one at a time, as the GRU regulariser delivers them;
+            for k in range(s["d"]):            # depthnets._Stream folds STREAM_BATCH_PLANES of them in per launch
+                held.append(s["logits"][k])
+                if len(held) == batch_planes or k == s["d"] - 1:
+                    r = sweep.depth_regress(held, hyps, softmax_mode=sweep.SOFTMAX_RAW_EXP, d_begin=k + 1 - len(held),
+                                            num_depth=s["d"], state=s["state"], finalize=(k == s["d"] - 1))
+                    held = []
             depth = r["depth"]
             del sim
             mark("s%d_end" % (i + 1))
@@ -556,7 +561,8 @@ def run_cascade(args):
         "config": {"workload": "AdaMVS 3-stage cascade V=5 at 1856x2752: C/D = 32/48 @1/4, 16/32 @1/2, 8/8 @full; "
                                "pair volumes + weighted product + streaming soft-argmax + resampling",
                    "voxels_per_view": vox, "algorithmic_bytes_per_view": sum(bytes_stage),
-                   "l2": "every volume (1.3-2.6 GB) exceeds the 126 MB L2", "views_per_step_per_gpu": 1},
+                   "l2": "every volume (1.3-2.6 GB) exceeds the 126 MB L2", "views_per_step_per_gpu": 1,
+                   "stream_batch_planes": batch_planes},
         "ref_views_per_s": world * 1e3 / ms_step, "kernel_ms": kernel_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "weighted-product sweep, stage %d" % (dom + 1),

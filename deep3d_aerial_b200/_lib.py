@@ -44,6 +44,7 @@ class RegressArgs(C.Structure):
         ("logits", _f32p), ("logits_stride_d", C.c_int64), ("hyps", _f32p),
         ("depth", _f32p), ("conf", _f32p), ("index", _f32p), ("state", _f32p),
         ("exp_variance", _f32p), ("next_hyps", _f32p),
+        ("logit_planes", C.c_void_p * 16),
     ]
 
 
@@ -59,6 +60,7 @@ class SamplesArgs(C.Structure):
 
 
 FUSE_MAX_SRC, FUSE_GEOM_DOUBLES = 16, 64
+REGRESS_MAX_PLANES = 16
 
 
 class FuseArgs(C.Structure):

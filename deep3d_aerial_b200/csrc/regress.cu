@@ -33,6 +33,7 @@ struct RegressParams {
     float next_half_span;   // (float)(next_nd/2 * interval), module.py:619-620
     float lamb;
     float scale_h, scale_w; // hh/H, hw/W for the align_corners=False resize
+    const float* planes[D3D_REGRESS_MAX_PLANES];   // scattered [H,W] planes of the slice (logits == nullptr)
 };
 
 constexpr int kGroup = 8;
@@ -176,7 +177,8 @@ __global__ void __launch_bounds__(256) regress_rawexp_kernel(const RegressParams
         for (int j = 0; j < kGroup; ++j) {
             int k = k0 + j;
             bool ok = k < p.d_count;
-            x[j] = ok ? __ldg(lg + (size_t)k * p.stride_d) : -INFINITY;
+            const float* src = p.logits ? lg + (size_t)k * p.stride_d : p.planes[ok ? k : 0] + pix;
+            x[j] = ok ? __ldg(src) : -INFINITY;
             d[j] = ok ? hyp_at<HYPS>(p, p.d_begin + k, pix, tap) : 0.f;
         }
 #pragma unroll
@@ -228,7 +230,14 @@ extern "C" int d3d_depth_regress(const D3dRegressArgs* a, void* cuda_stream) {
                     a->height, a->width);
     if ((long long)a->height * a->width > INT32_MAX)
         return fail(D3D_ERR_UNSUPPORTED, "d3d_depth_regress: H*W exceeds 2^31-1");
-    if (!a->logits || !a->hyps) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: logits/hyps is NULL");
+    if (!a->hyps) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: hyps is NULL");
+    if (!a->logits) {                                   // scattered planes: streaming flavours only
+        if (a->softmax_mode == D3D_SOFTMAX_STABLE || a->d_count <= 0 || a->d_count > D3D_REGRESS_MAX_PLANES)
+            return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: logits is NULL (logit_planes need RAW_EXP / NONE and "
+                        "1 <= d_count <= %d)", D3D_REGRESS_MAX_PLANES);
+        for (int k = 0; k < a->d_count; ++k)
+            if (!a->logit_planes[k]) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: logit_planes[%d] is NULL", k);
+    }
     if (a->softmax_mode < D3D_SOFTMAX_STABLE || a->softmax_mode > D3D_SOFTMAX_NONE)
         return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_regress: unknown softmax_mode %d", a->softmax_mode);
     if (a->conf_mode != D3D_CONF_MAX_PROB && a->conf_mode != D3D_CONF_WINDOW4)
@@ -273,6 +282,7 @@ extern "C" int d3d_depth_regress(const D3dRegressArgs* a, void* cuda_stream) {
     p.lamb = a->lamb;
     p.scale_h = p.hh > 0 ? (float)p.hh / (float)p.H : 1.f;
     p.scale_w = p.hw > 0 ? (float)p.hw / (float)p.W : 1.f;
+    for (int k = 0; k < D3D_REGRESS_MAX_PLANES; ++k) p.planes[k] = (!a->logits && k < d_count) ? a->logit_planes[k] : nullptr;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     switch (a->hyps_mode) {
         case D3D_HYPS_UNIFORM: return launch_regress<D3D_HYPS_UNIFORM>(p, a->softmax_mode, stream);

@@ -110,22 +110,38 @@ def red_depthnet_forward(self, features, proj_matrices, depth_values, num_depth,
     return {"depth": r["depth"], "photometric_confidence": r["conf"]}
 
 
+# Planes of regulariser output folded into the streaming soft-argmax accumulators per launch.  Upstream updates
+# its three accumulator maps after every plane (adamvs.py:514-525) because the whole design streams through an
+# 11 GB GPU; on a B200 the last K planes simply stay alive (K x 20 MB at 1856 x 2752) and ONE launch folds them in,
+# in plane order with the same fp32 operations -- bit-identical, and the accumulators are read and written once per
+# K planes instead of once per plane (145 -> 33 MB of HBM traffic per plane at the stage-2 shape).  1 = upstream's
+# cadence.  At most 16 (D3D_REGRESS_MAX_PLANES).
+STREAM_BATCH_PLANES = 16
+
+
 class _Stream:
     """Streaming soft-argmax accumulators of the plane-at-a-time models (adamvs.py:456-462, 514-529)."""
 
     def __init__(self, batch, h, w, device):
         self.state = [torch.zeros((3, h, w), device=device, dtype=torch.float32) for _ in range(batch)]
+        self.pending = [[] for _ in range(batch)]
         self.out = None
 
     def update(self, d, num_depth, reg_cost, depth_values):
         """reg_cost [B,1,H,W] = the regulariser's output for plane d."""
         last = d == num_depth - 1
+        k = max(1, min(int(STREAM_BATCH_PLANES), 16))
         outs = []
         for b in range(reg_cost.shape[0]):
-            outs.append(sweep.depth_regress(reg_cost[b], depth_values[b].contiguous(), softmax_mode=sweep.SOFTMAX_RAW_EXP,
-                                            d_begin=d, state=self.state[b], finalize=last))
+            held = self.pending[b]
+            held.append(reg_cost[b, 0])
+            if len(held) < k and not last:
+                continue
+            outs.append(sweep.depth_regress(list(held), depth_values[b].contiguous(), softmax_mode=sweep.SOFTMAX_RAW_EXP,
+                                            d_begin=d + 1 - len(held), state=self.state[b], finalize=last))
+            held.clear()
         if last:
-            self.out = {k: torch.stack([o[k] for o in outs], 0) for k in ("depth", "conf")}
+            self.out = {k_: torch.stack([o[k_] for o in outs], 0) for k_ in ("depth", "conf")}
 
 
 def red_infer_forward(self, features, proj_matrices, depth_values, num_depth, cost_regularization):

@@ -61,14 +61,24 @@ class PlaneLoop:
 
     def _run(self):
         states = [torch.zeros(s, device=self.dev) for s in self.state_shapes]          # adamvs.py:451-452
+        from .depthnets import STREAM_BATCH_PLANES
+        k = max(1, min(int(STREAM_BATCH_PLANES), 16))          # planes folded into the accumulators per launch
         depth = conf = None
+        held = [[] for _ in range(self.batch)]
         for d in range(self.planes):
             out = self.step(self.volume[:, d], *states)
             reg_cost, states = out[0], list(out[1:])
             last = d == self.planes - 1
-            res = [sweep.depth_regress(reg_cost[b], self.hyps[b], softmax_mode=sweep.SOFTMAX_RAW_EXP, d_begin=d,
-                                       num_depth=self.planes, state=self._acc[b], finalize=last)
+            for b in range(self.batch):
+                held[b].append(reg_cost[b, 0])
+            if len(held[0]) < k and not last:
+                continue
+            res = [sweep.depth_regress(list(held[b]), self.hyps[b], softmax_mode=sweep.SOFTMAX_RAW_EXP,
+                                       d_begin=d + 1 - len(held[b]), num_depth=self.planes, state=self._acc[b],
+                                       finalize=last)
                    for b in range(self.batch)]
+            for b in range(self.batch):
+                held[b].clear()
             if last:
                 depth = torch.stack([r["depth"] for r in res], 0)
                 conf = torch.stack([r["conf"] for r in res], 0)

@@ -172,16 +172,32 @@ def depth_regress(logits: torch.Tensor, hyps: torch.Tensor, *, conf_mode: int = 
     hyps: [D] (uniform), [D,H,W] (per pixel) or [D,h',w'] (bilinearly resized to H x W, align_corners
     False).  Returns a dict with "depth", "conf" and optionally "index", "exp_variance", "next_hyps",
     "state".  With softmax_mode=SOFTMAX_RAW_EXP the call may cover a slice of planes starting at
-    d_begin and carries its accumulators in `state` [3,H,W].
+    d_begin and carries its accumulators in `state` [3,H,W]; the slice may then also be a LIST of up to 16
+    separately allocated [H,W] planes (what a plane-at-a-time regulariser returns call after call).
     """
+    planes = None
+    if isinstance(logits, (list, tuple)):
+        if softmax_mode == SOFTMAX_STABLE or not 1 <= len(logits) <= _lib.REGRESS_MAX_PLANES:
+            raise ValueError("a list of planes needs RAW_EXP / NONE and 1..%d entries" % _lib.REGRESS_MAX_PLANES)
+        planes = []
+        for t in logits:
+            if not t.is_cuda or t.dtype != torch.float32:
+                raise RuntimeError("logits must be fp32 CUDA tensors (no CPU fallback)")
+            if t.dim() < 2 or t.numel() != t.shape[-2] * t.shape[-1] or (planes and t.shape[-2:] != planes[0].shape):
+                raise ValueError("every plane must be one [H,W] map of the same extent")
+            planes.append(t.reshape(t.shape[-2], t.shape[-1]).contiguous())
+        logits = planes[0].unsqueeze(0)
+        dn_list = len(planes)
     if logits.dim() != 3:
         raise ValueError("logits must be [D,H,W]")
     if not logits.is_cuda or logits.dtype != torch.float32:
         raise RuntimeError("logits must be an fp32 CUDA tensor (no CPU fallback)")
     dn, h, w = logits.shape
+    if planes is not None:
+        dn = dn_list
     if logits.stride(2) != 1 or logits.stride(1) != w:
         logits = logits.contiguous()
-    stride_d = logits.stride(0) if dn > 1 else h * w
+    stride_d = logits.stride(0) if dn > 1 and planes is None else h * w
     hyps = _need(hyps, "hyps")
     d = int(num_depth) if num_depth is not None else hyps.shape[0]
     if hyps.shape[0] != d:
@@ -221,7 +237,10 @@ def depth_regress(logits: torch.Tensor, hyps: torch.Tensor, *, conf_mode: int = 
     a.next_num_depth = next_num_depth if do_final else 0
     a.next_interval = float(next_interval)
     a.lamb = float(lamb) if lamb is not None else 0.0
-    a.logits, a.logits_stride_d, a.hyps = logits.data_ptr(), stride_d, hyps.data_ptr()
+    a.logits, a.logits_stride_d, a.hyps = (logits.data_ptr() if planes is None else None), stride_d, hyps.data_ptr()
+    if planes is not None:
+        for k, t in enumerate(planes):
+            a.logit_planes[k] = t.data_ptr()
     a.depth, a.conf, a.index = _ptr(res.get("depth")), _ptr(res.get("conf")), _ptr(res.get("index"))
     a.state, a.exp_variance, a.next_hyps = _ptr(state), _ptr(res.get("exp_variance")), _ptr(res.get("next_hyps"))
     with torch.cuda.device(dev):

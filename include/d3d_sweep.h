@@ -104,6 +104,8 @@ enum { D3D_HYPS_UNIFORM = 0,   /* hyps[D]                                       
        D3D_HYPS_RESIZED = 2    /* hyps[D,hyps_height,hyps_width] bilinearly resized to H x W with
                                   align_corners=False (module.py:608-610, adamvs.py:519-520)        */ };
 
+#define D3D_REGRESS_MAX_PLANES 16
+
 typedef struct D3dRegressArgs {
     uint32_t struct_size;
     int32_t num_depth;        /* D: planes of the whole sweep                                     */
@@ -130,6 +132,12 @@ typedef struct D3dRegressArgs {
                                  all D planes                                                      */
     float* exp_variance;      /* [H,W] lamb*sqrt(sum p (d-depth)^2), STABLE only; NULL = skip     */
     float* next_hyps;         /* [next_num_depth,H,W]: depth -/+ next_num_depth/2*next_interval   */
+    const float* logit_planes[D3D_REGRESS_MAX_PLANES]; /* RAW_EXP / NONE only, used when `logits` is NULL:
+                                 plane d_begin+k of the slice is the [H,W] map logit_planes[k] (k < d_count
+                                 <= D3D_REGRESS_MAX_PLANES).  Lets a caller whose regulariser hands back one
+                                 freshly allocated plane per call (adamvs.py:512, msrednet.py:416) keep K
+                                 planes alive and fold them into the accumulators with ONE launch: the
+                                 3-map state is then read and written once per K planes, not once per plane */
 } D3dRegressArgs;
 
 /* Fused softmax over D + expected depth + confidence (+ argmax, + UCS-Net spread, + next-stage

@@ -434,6 +434,48 @@ def test_streaming_raw_exp_matches_oracle_slice_by_slice():
     assert _depth_err(whole["depth"], want_d[0]) < DEPTH_TOL
 
 
+@pytest.mark.parametrize("group", [1, 3, 5, 16])
+def test_streaming_raw_exp_scattered_planes_are_bit_identical_to_plane_at_a_time(group):
+    """D3dRegressArgs.logit_planes: K separately allocated planes folded into the accumulators by one launch give
+    the very bytes K single-plane launches give (same fp32 operations in the same plane order)."""
+    d, h, w = 37, 22, 30
+    lg = (0.5 * synth.planted_logits(d, 2 * h, 2 * w, seed=9)).to(DEV)
+    hy = synth.per_pixel_hypotheses(synth.smooth_depth_map(synth.make_rig(), h, w), d, 4.0).to(DEV)
+    state1 = torch.zeros(3, 2 * h, 2 * w, device=DEV)
+    for k in range(d):
+        one = sweep.depth_regress(lg[k:k + 1], hy, softmax_mode=sweep.SOFTMAX_RAW_EXP, d_begin=k, state=state1,
+                                  finalize=(k == d - 1))
+    stateg = torch.zeros(3, 2 * h, 2 * w, device=DEV)
+    for k0 in range(0, d, group):
+        planes = [lg[k].clone().view(1, 2 * h, 2 * w) for k in range(k0, min(k0 + group, d))]   # scattered allocations
+        many = sweep.depth_regress(planes, hy, softmax_mode=sweep.SOFTMAX_RAW_EXP, d_begin=k0, state=stateg,
+                                   finalize=(k0 + group >= d))
+    assert torch.equal(many["depth"], one["depth"]) and torch.equal(many["conf"], one["conf"])
+    assert torch.equal(stateg, state1)
+    with pytest.raises(ValueError, match="1..16"):
+        sweep.depth_regress([lg[0]] * 17, hy, softmax_mode=sweep.SOFTMAX_RAW_EXP, d_begin=0, state=stateg)
+    with pytest.raises(ValueError, match="RAW_EXP"):
+        sweep.depth_regress([lg[0]], hy, softmax_mode=sweep.SOFTMAX_STABLE)
+
+
+@pytest.mark.parametrize("batch_planes", [1, 4, 16])
+def test_stream_batch_cadence_does_not_change_the_plane_at_a_time_models(batch_planes, monkeypatch):
+    """depthnets.STREAM_BATCH_PLANES only changes how often the accumulators travel: AdaMVS and RED-Net inference
+    forwards give identical bytes at every cadence (1 = upstream's per-plane update)."""
+    def run(k):
+        monkeypatch.setattr(depthnets, "STREAM_BATCH_PLANES", k)
+        g = load_golden("ada_infer_depthnet")
+        ada = depthnets.ada_infer_forward(_Ada(in_up=True), _cuda_views(g["feats"]), g["proj"].to(DEV), g["hyps"].to(DEV),
+                                          g["hyps"].shape[1])
+        g = load_golden("red_infer_depthnet")
+        red = depthnets.REDInferDepthNet()(_cuda_views(g["feats"]), g["proj"].to(DEV), g["hyps"].to(DEV),
+                                           g["hyps"].shape[1], standins.slice_reg_red)
+        return ada["depth"], ada["photometric_confidence"], red["depth"], red["photometric_confidence"]
+    base = run(1)
+    got = run(batch_planes)
+    assert all(torch.equal(a, b) for a, b in zip(base, got))
+
+
 def test_exp_variance_matches_oracle():
     d, h, w = 8, 24, 24
     logits = synth.planted_logits(d, h, w, seed=6) * 0.3
