@@ -196,3 +196,29 @@ def test_predict_driver_writes_the_reference_outputs(workspace, tmp_path):
         want_depth, want_conf = want_depth[0].numpy(), want_conf[0].numpy()
         assert np.abs(depth - want_depth).max() / np.abs(want_depth).max() < 1e-3          # north_star: depth 1e-3
         assert np.abs(prob - want_conf).max() < 1e-3
+
+
+def test_mvs_inference_drop_in_builds_the_predict_command(tmp_path, capsys, monkeypatch):
+    """`mvs/mvs_dl.py:MVS_Inference` with the same signature: default checkpoint lookup, the command line of
+    predict.py (same option names), launched through os.system with its status ignored."""
+    from deep3d_aerial_b200 import mvs_dl, predict
+    ref = tmp_path / "mvs_cas"
+    ck = ref / "checkpoints" / "adamvs" / "whu_omvs"
+    ck.mkdir(parents=True)
+    (ck / "notes.txt").write_text("x")
+    (ck / "model_000019.ckpt").write_text("x")
+    mi = mvs_dl.MVS_Inference(2752, 1856, 5, 384, 0.1, 'AdaMVS', None, False, reference_root=str(ref))
+    cmd = mi.command("/ws/export", "/ws/dense/MVS")
+    assert "-m deep3d_aerial_b200.predict" in cmd and "--loadckpt=" + str(ck / "model_000019.ckpt") in cmd
+    argv = cmd.split(" -m deep3d_aerial_b200.predict ")[1].split()
+    args = predict.build_parser().parse_args(argv)                       # every option is one predict accepts
+    assert (args.model, args.view_num, args.numdepth, args.max_w, args.max_h) == ("adamvs", 5, 384, 2752, 1856)
+    assert args.data_folder == "/ws/export" and args.output_folder == "/ws/dense/MVS" and args.display == "False"
+    multi = mvs_dl.MVS_Inference(2752, 1856, pretrain_weight="w.ckpt", gpus=8, feature_cache=64).command("a", "b")
+    assert "--nproc-per-node 8" in multi and "--master-addr 127.0.0.1" in multi and "--partition=contiguous" in multi
+    with pytest.raises(Exception, match="Not implemented"):
+        mvs_dl.MVS_Inference(1, 1, model_type="colmap").command("a", "b")
+    ran = []
+    monkeypatch.setattr(mvs_dl.os, "system", lambda c: ran.append(c) or 1)   # a failing launch is ignored, as upstream
+    mi.run("/ws/export", str(tmp_path / "dense" / "MVS"))
+    assert ran == [mi.command("/ws/export", str(tmp_path / "dense" / "MVS"))] and (tmp_path / "dense").is_dir()
