@@ -488,10 +488,11 @@ def run_cascade(args):
         for i, s in enumerate(stages):
             mark("s%d_begin" % (i + 1))
             tex = sweep.to_texels(s["feats"])
+            rays = sweep.reference_rays(s["pose"], s["h"], s["w"])      # once per stage (depthnets._scene)
             if depth is None:
                 hyps = sweep.depth_samples(sweep.SAMPLES_RANGE, s["d"], (s["h"], s["w"]), device=dev,
                                            dmin=rig.dmin, dmax=rig.dmax)
-                pairs = sweep.cost_volume(tex, s["pose"], hyps, sweep.AGG_PAIR_MEAN)
+                pairs = sweep.cost_volume(tex, s["pose"], hyps, sweep.AGG_PAIR_MEAN, rays=rays)
                 conf = torch.stack([sweep.depth_regress(pair_logits[k], hyps, want_index=False)["conf"]
                                     for k in range(v - 1)], 0)
                 del pairs
@@ -501,7 +502,7 @@ def run_cascade(args):
                 conf = F.interpolate(conf.unsqueeze(0), [s["h"], s["w"]], mode="bilinear", align_corners=False)[0]
             mark("s%d_sweep" % (i + 1))
             sim = sweep.cost_volume(tex, s["pose"], hyps, sweep.AGG_WEIGHTED_PRODUCT, weights=conf.contiguous(),
-                                    plane_major=True)
+                                    plane_major=True, rays=rays)
             mark("s%d_regress" % (i + 1))
             r = None
             held = []                          # planes arrive one at a time, as the GRU regulariser delivers them;

@@ -40,13 +40,13 @@ def _plane_loop(owner, tag, step, batch, planes, channels, hw, out_hw, state_sha
     return cache[key]
 
 
-def _volume_into(out, features, proj_matrices, depth_values, mode, **kw):
+def _volume_into(out, features, proj_matrices, depth_values, mode, scenes=None, **kw):
     """Plane-major cost volume of every batch item written straight into `out` [B,D,C,h,w]."""
     with torch.no_grad():
         for b in range(features[0].shape[0]):
-            texels, pose = _scene(features, proj_matrices, b)
+            texels, pose, rays = scenes[b] if scenes is not None else _scene(features, proj_matrices, b)
             w = kw.get("weights")
-            sweep.cost_volume(texels, pose, depth_values[b].contiguous(), mode, plane_major=True, out=out[b],
+            sweep.cost_volume(texels, pose, depth_values[b].contiguous(), mode, plane_major=True, out=out[b], rays=rays,
                               **{**kw, "weights": None if w is None else w[b]})
 
 
@@ -57,21 +57,25 @@ def _check(features, proj_matrices, depth_values, num_depth):
 
 
 def _scene(features, proj_matrices, b):
-    """Channels-last texels [V,H,W,C] and relative poses [V-1,4,4] of batch item b."""
-    texels = sweep.to_texels([f[b] for f in features])
-    pose = sweep.relative_poses(torch.stack([p[b] for p in proj_matrices], 0))
-    return texels, pose
+    """What every sweep over one stage of batch item b shares: channels-last texels [V,H,W,C], relative poses
+    [V-1,4,4] and the reference's own rays rot @ [x,y,1] [V-1,3,H*W] (sweep.reference_rays).  AdaMVS sweeps a stage
+    twice (pair volumes, then the weighted product): it builds the scene once."""
+    with torch.no_grad():
+        texels = sweep.to_texels([f[b] for f in features])
+        pose = sweep.relative_poses(torch.stack([p[b] for p in proj_matrices], 0))
+        rays = sweep.reference_rays(pose, texels.shape[1], texels.shape[2])
+    return texels, pose, rays
 
 
-def _volume(features, proj_matrices, depth_values, mode, plane_major=False, **kw):
+def _volume(features, proj_matrices, depth_values, mode, plane_major=False, scenes=None, **kw):
     """Cost volume for every batch item: [B,Cout,D,H,W] (or [B,D,Cout,H,W] plane-major)."""
     with torch.no_grad():
         vols = []
         for b in range(features[0].shape[0]):
-            texels, pose = _scene(features, proj_matrices, b)
+            texels, pose, rays = scenes[b] if scenes is not None else _scene(features, proj_matrices, b)
             w = kw.get("weights")
             vols.append(sweep.cost_volume(texels, pose, depth_values[b].contiguous(), mode, plane_major=plane_major,
-                                          **{**kw, "weights": None if w is None else w[b]}))
+                                          rays=rays, **{**kw, "weights": None if w is None else w[b]}))
         return torch.stack(vols, 0) if len(vols) > 1 else vols[0].unsqueeze(0)
 
 
@@ -185,9 +189,10 @@ def ada_infer_forward(self, features, proj_matrices, depth_values, num_depth, co
     state2 = torch.zeros((b_num, 16, int(img_h / 2), int(img_w / 2)), device=dev)
     up = 2 if self.in_up else 1
     acc = _Stream(b_num, img_h * up, img_w * up, dev)
+    scenes = [_scene(features, proj_matrices, b) for b in range(b_num)]
 
     if confidence_map is None:                                                                  # :465-489
-        pairs = _volume(features, proj_matrices, depth_values, sweep.AGG_PAIR_MEAN)              # [B,V-1,D,h,w]
+        pairs = _volume(features, proj_matrices, depth_values, sweep.AGG_PAIR_MEAN, scenes=scenes)   # [B,V-1,D,h,w]
         for i in range(n_src):
             score_volume = self.reg(pairs[:, i])
             with torch.no_grad():
@@ -205,7 +210,8 @@ def ada_infer_forward(self, features, proj_matrices, depth_values, num_depth, co
         loop = _plane_loop(self, "ada", self.reg_fuse, b_num, num_depth, ref.shape[1], (img_h, img_w),
                            (img_h * up, img_w * up), [tuple(state1.shape), tuple(state2.shape)],
                            tuple(depth_values.shape[2:]), dev)
-        _volume_into(loop.volume, features, proj_matrices, depth_values, sweep.AGG_WEIGHTED_PRODUCT, weights=weights)
+        _volume_into(loop.volume, features, proj_matrices, depth_values, sweep.AGG_WEIGHTED_PRODUCT, weights=weights,
+                     scenes=scenes)
         loop.hyps.copy_(depth_values)
         depth, conf = loop.replay()
         for d in range(num_depth):
@@ -213,7 +219,7 @@ def ada_infer_forward(self, features, proj_matrices, depth_values, num_depth, co
         return {"depth": depth.clone(), "photometric_confidence": conf.clone(),
                 "pair_confidence": pair_confidence, "pair_result": pair_results}
     similarity = _volume(features, proj_matrices, depth_values, sweep.AGG_WEIGHTED_PRODUCT, plane_major=True,
-                         weights=weights)                                                        # [B,D,C,h,w]
+                         weights=weights, scenes=scenes)                                         # [B,D,C,h,w]
     for d in range(num_depth):
         pair_confidence.extend(resized)
         reg_cost, state1, state2 = self.reg_fuse(similarity[:, d], state1, state2)               # :512
@@ -230,8 +236,9 @@ def ada_depthnet_forward(self, features, proj_matrices, depth_values, num_depth,
     n_src = len(features) - 1
     _, _, img_h, img_w = features[0].shape
     pair_confidence, pair_results = [], []
+    scenes = [_scene(features, proj_matrices, b) for b in range(features[0].shape[0])]
     if confidence_map is None:
-        pairs = _volume(features, proj_matrices, depth_values, sweep.AGG_PAIR_MEAN)
+        pairs = _volume(features, proj_matrices, depth_values, sweep.AGG_PAIR_MEAN, scenes=scenes)
         for i in range(n_src):
             score_volume = self.reg(pairs[:, i])
             r = _regress(score_volume, depth_values, conf_mode=sweep.CONF_MAX_PROB, want_index=False)
@@ -244,7 +251,7 @@ def ada_depthnet_forward(self, features, proj_matrices, depth_values, num_depth,
         pair_confidence.extend(resized)
         weights = torch.cat(resized, 1)
     fused = _volume(features, proj_matrices, depth_values, sweep.AGG_WEIGHTED_PRODUCT, weights=weights,
-                    eps_in_numerator=True)
+                    eps_in_numerator=True, scenes=scenes)
     prob_volume_pre = self.reg_fuse(fused).squeeze(1)
     r = _regress(prob_volume_pre, depth_values, conf_mode=sweep.CONF_MAX_PROB, want_index=False)
     return {"depth": r["depth"], "photometric_confidence": r["conf"], "pair_confidence": pair_confidence,
