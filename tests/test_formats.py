@@ -150,16 +150,26 @@ def test_predict_driver_writes_the_reference_outputs(workspace, tmp_path):
     from deep3d_aerial_b200 import depthnets, module as d3d_module, predict
     from oracle import standins, sweep_torch
 
-    class TinyCascade(nn.Module):                          # one stage at 1/4 resolution, 8 fixed "feature" channels
+    class TinyFeatureNet(nn.Module):                       # 8 fixed "feature" channels at 1/4 resolution
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(0)
+            self.register_buffer("kernel", torch.randn(8, 3, 3, 3, generator=g) * 0.3)
+            self.calls = 0
+
+        def forward(self, img):
+            self.calls += 1
+            return F.avg_pool2d(F.conv2d(img, self.kernel, padding=1), 4)
+
+    class TinyCascade(nn.Module):                          # one stage, the reference's walk over imgs[:, v]
         def __init__(self, num_depth):
             super().__init__()
             self.num_depth = num_depth
             self.depthnet = depthnets.DepthNet()
-            g = torch.Generator().manual_seed(0)
-            self.register_buffer("kernel", torch.randn(8, 3, 3, 3, generator=g) * 0.3)
+            self.feature = TinyFeatureNet()
 
         def features(self, imgs):
-            return [F.avg_pool2d(F.conv2d(imgs[:, v], self.kernel, padding=1), 4) for v in range(imgs.shape[1])]
+            return [self.feature(imgs[:, v]) for v in range(imgs.shape[1])]
 
         def forward(self, imgs, proj_matrices, depth_values):
             feats = self.features(imgs)
@@ -173,10 +183,13 @@ def test_predict_driver_writes_the_reference_outputs(workspace, tmp_path):
 
     out_dir = str(tmp_path / "dense")
     args = predict.build_parser().parse_args(["--data_folder", workspace, "--output_folder", out_dir, "--view_num", "3",
-                                              "--numdepth", "16", "--max_h", "64", "--max_w", "96"])
+                                              "--numdepth", "16", "--max_h", "64", "--max_w", "96",
+                                              "--feature_cache", "8"])
     model = TinyCascade(16)
     written = predict.predict_depth(args, model=model)
     assert len(written) == 3
+    assert model.feature.calls == 4          # 3 reference views x 3 images, 4 distinct images: each encoded once (row f4)
+    model.feature.calls = 0
     ds = dataset.MVSDataset(workspace, "val", 3, "mean", args)
     for idx, paths in enumerate(written):
         depth, _ = formats.load_pfm_utf8(paths["depth"])
