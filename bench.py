@@ -321,7 +321,7 @@ def run_ours(args):
         feats, proj, hyps, logits = slots[i % 2]
         sweep.to_texels(feats, out=texels)
         pose = sweep.relative_poses(proj)                       # module.py:528, per source view
-        rays = sweep.reference_rays(pose, h, w)                 # module.py:538 (bit-identical rays at any size)
+        rays = sweep.rays_for(pose, h, w)                       # module.py:538 where the kernel's order differs
         if events:
             events[0].record()
         sweep.cost_volume(texels, pose, hyps, agg, groups=groups, out=volume, variant=args.variant, rays=rays)
@@ -488,7 +488,7 @@ def run_cascade(args):
         for i, s in enumerate(stages):
             mark("s%d_begin" % (i + 1))
             tex = sweep.to_texels(s["feats"])
-            rays = sweep.reference_rays(s["pose"], s["h"], s["w"])      # once per stage (depthnets._scene)
+            rays = sweep.rays_for(s["pose"], s["h"], s["w"])            # once per stage (depthnets._scene)
             if depth is None:
                 hyps = sweep.depth_samples(sweep.SAMPLES_RANGE, s["d"], (s["h"], s["w"]), device=dev,
                                            dmin=rig.dmin, dmax=rig.dmax)

@@ -84,6 +84,7 @@ EXPORTS = {
     "d3d_depth_regress": (C.c_int, [C.POINTER(RegressArgs), C.c_void_p]),
     "d3d_depth_samples": (C.c_int, [C.POINTER(SamplesArgs), C.c_void_p]),
     "d3d_consistency_fuse": (C.c_int, [C.POINTER(FuseArgs), C.c_void_p]),
+    "d3d_pixel_rays": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "d3d_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "d3d_last_error": (C.c_char_p, []),
     "d3d_version": (C.c_int, []),

@@ -169,6 +169,28 @@ extern "C" int d3d_depth_samples(const D3dSamplesArgs* a, void* cuda_stream) {
     return check_launch("depth_samples_kernel");
 }
 
+// rot @ [x,y,1] in the order the sweep kernels use when they form the rays themselves (sweep_quad.cuh, sweep_direct.cuh)
+__global__ void __launch_bounds__(256) pixel_rays_kernel(const float* __restrict__ pose, int W, int HW, float* __restrict__ out) {
+    const int pix = blockIdx.x * 256 + threadIdx.x;
+    if (pix >= HW) return;
+    const int py = pix / W, px = pix - py * W;
+    const float* m = pose + blockIdx.y * 16;
+    float* o = out + (size_t)blockIdx.y * 3 * HW + pix;
+    o[0] = fmaf(m[2], 1.f, fmaf(m[1], (float)py, m[0] * (float)px));
+    o[HW] = fmaf(m[6], 1.f, fmaf(m[5], (float)py, m[4] * (float)px));
+    o[2 * (size_t)HW] = fmaf(m[10], 1.f, fmaf(m[9], (float)py, m[8] * (float)px));
+}
+
+extern "C" int d3d_pixel_rays(const float* pose, int32_t num_src, int32_t height, int32_t width, float* out, void* cuda_stream) {
+    if (!pose || !out) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_pixel_rays: pose/out is NULL");
+    if (num_src < 1 || num_src > 65535 || height < 1 || width < 1 || (long long)height * width > INT32_MAX / 2)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_pixel_rays: bad extent V-1=%d H=%d W=%d", num_src, height, width);
+    const int hw = height * width;
+    pixel_rays_kernel<<<dim3((hw + 255) / 256, num_src), 256, 0, (cudaStream_t)cuda_stream>>>(pose, width, hw, out);
+    count_launch();
+    return check_launch("pixel_rays_kernel");
+}
+
 extern "C" int d3d_nchw_to_nhwc(const float* in, float* out, int32_t channels, int32_t height, int32_t width,
                                 void* cuda_stream) {
     if (!in || !out) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_nchw_to_nhwc: NULL pointer");

@@ -58,12 +58,12 @@ def _check(features, proj_matrices, depth_values, num_depth):
 
 def _scene(features, proj_matrices, b):
     """What every sweep over one stage of batch item b shares: channels-last texels [V,H,W,C], relative poses
-    [V-1,4,4] and the reference's own rays rot @ [x,y,1] [V-1,3,H*W] (sweep.reference_rays).  AdaMVS sweeps a stage
+    [V-1,4,4] and the rays rot @ [x,y,1] [V-1,3,H*W] where the kernels cannot form them bit-exactly (sweep.rays_for).  AdaMVS sweeps a stage
     twice (pair volumes, then the weighted product): it builds the scene once."""
     with torch.no_grad():
         texels = sweep.to_texels([f[b] for f in features])
         pose = sweep.relative_poses(torch.stack([p[b] for p in proj_matrices], 0))
-        rays = sweep.reference_rays(pose, texels.shape[1], texels.shape[2])
+        rays = sweep.rays_for(pose, texels.shape[1], texels.shape[2])
     return texels, pose, rays
 
 

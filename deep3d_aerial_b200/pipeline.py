@@ -67,7 +67,7 @@ class ViewPipeline:
             # camera geometry of this view (the reference's own torch calls, module.py:528 and :538) also runs on
             # the copy stream, i.e. behind the previous view's sweep; the slot keeps the tensors alive
             s["pose"] = sweep.relative_poses(s["proj"])
-            s["rays"] = sweep.reference_rays(s["pose"], self.shape[2], self.shape[3])
+            s["rays"] = sweep.rays_for(s["pose"], self.shape[2], self.shape[3])
             s["copied"].record()
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(s["copied"])

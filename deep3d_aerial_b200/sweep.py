@@ -97,6 +97,41 @@ def reference_rays(pose: torch.Tensor, h: int, w: int) -> torch.Tensor:
     return rays
 
 
+def kernel_rays(pose: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """[V-1,3,H*W] rays as the sweep kernels form them when none are handed in: fma(r2, 1, fma(r1, y, r0*x))."""
+    pose = _need(pose, "pose")
+    out = torch.empty((pose.shape[0], 3, h * w), device=pose.device, dtype=torch.float32)
+    with torch.cuda.device(pose.device):
+        _lib.check(_lib.load().d3d_pixel_rays(pose.data_ptr(), pose.shape[0], h, w, out.data_ptr(), _stream()))
+    return out
+
+
+# (H, W, device) -> does cuBLAS round the reference's rot @ [x,y,1] in the kernels' own order at this size?
+_RAY_ORDER = {}
+_PROBE = ((0.9931, -0.0713, 13.71, 0.0), (0.0527, 1.0117, -22.37, 0.0), (1.3e-5, -2.1e-5, 1.0031, 0.0), (0.0, 0.0, 0.0, 1.0))
+
+
+def rays_for(pose: torch.Tensor, h: int, w: int) -> Optional[torch.Tensor]:
+    """The `rays` argument of `cost_volume` for this pose: None where the kernels' own rays are bit-identical to the
+    reference's matmul, else `reference_rays(pose, h, w)`.
+
+    Which it is depends on the kernel cuBLAS picks for a [1,3,3] @ [1,3,H*W] product, i.e. on the image size, not
+    on the values: the first call at a size computes both forms, for a generic dense probe rotation AND for the
+    pose at hand, and compares them bit for bit (one host sync per size and device, so call it outside CUDA-graph
+    capture); every later call at that size reuses the verdict.  At 1856 x 2752 the skipped matmuls are 0.9 ms of
+    a 10.7 ms AdaMVS view."""
+    key = (h, w, pose.device.index)
+    same = _RAY_ORDER.get(key)
+    if same is None:
+        probe = torch.tensor(_PROBE, dtype=torch.float32, device=pose.device).unsqueeze(0)
+        ref = reference_rays(pose, h, w)
+        same = bool(torch.equal(reference_rays(probe, h, w), kernel_rays(probe, h, w))) and \
+            bool(torch.equal(ref, kernel_rays(pose, h, w)))
+        _RAY_ORDER[key] = same
+        return None if same else ref
+    return None if same else reference_rays(pose, h, w)
+
+
 def cost_volume(texels: torch.Tensor, pose: torch.Tensor, hyps: torch.Tensor, mode: int = AGG_VARIANCE, *,
                 groups: int = 0, weights: Optional[torch.Tensor] = None, eps_in_numerator: bool = False,
                 d_begin: int = 0, d_count: int = 0, out: Optional[torch.Tensor] = None,
@@ -104,8 +139,9 @@ def cost_volume(texels: torch.Tensor, pose: torch.Tensor, hyps: torch.Tensor, mo
                 exact_rays: bool = True) -> torch.Tensor:
     """Fused warp + aggregate.  texels [V,H,W,C]; pose [V-1,4,4]; hyps [D] or [D,H,W].
 
-    rays: `reference_rays(pose, H, W)` if the caller already has them (plane-slice callers compute them once
-    per view); with exact_rays (default) they are computed here, with exact_rays=False the kernel forms them.
+    rays: `rays_for(pose, H, W)` if the caller already has them (plane-slice callers compute them once per view);
+    with exact_rays (default) that call is made here -- the reference's own matmul wherever the kernel's rounding
+    order is not known to match it; with exact_rays=False the kernel forms them unconditionally.
 
     Returns [Cout, Dn, H, W] (or [Dn, Cout, H, W] with plane_major=True, the layout whose planes are
     contiguous [Cout,H,W] slices for the plane-at-a-time regularisers), Dn = planes computed.
@@ -147,7 +183,7 @@ def cost_volume(texels: torch.Tensor, pose: torch.Tensor, hyps: torch.Tensor, mo
     a.d_begin, a.d_count, a.hyps_per_pixel = d_begin, dn, per_pixel
     a.groups, a.eps_in_numerator, a.variant = groups, int(eps_in_numerator), variant
     if rays is None and exact_rays:
-        rays = reference_rays(pose, h, w)
+        rays = rays_for(pose, h, w)
     if rays is not None:
         rays = _need(rays, "rays")
         if tuple(rays.shape) != (v - 1, 3, h * w):

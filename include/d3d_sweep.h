@@ -168,6 +168,12 @@ typedef struct D3dSamplesArgs {
 /* Per-stage depth-hypothesis resampling, get_depth_range_samples (module.py:633-650). */
 int d3d_depth_samples(const D3dSamplesArgs* args, void* cuda_stream);
 
+/* out[V-1,3,H*W] = rot_i @ [x,y,1] for every reference pixel, rounded as the sweep kernels round it when
+ * D3dCostVolumeArgs.rays is NULL: fma(r2, 1, fma(r1, y, r0*x)).  The binding compares this with the reference's own
+ * torch.matmul (module.py:538) once per image size to learn whether cuBLAS rounds in that order at that size; where
+ * it does, the sweeps form their rays themselves and the matmul (a 0.75 TB/s skinny GEMM) is skipped. */
+int d3d_pixel_rays(const float* pose, int32_t num_src, int32_t height, int32_t width, float* out, void* cuda_stream);
+
 /* Feature relayout [C,H,W] -> [H,W,C] (the sweep kernel gathers whole texels). */
 int d3d_nchw_to_nhwc(const float* in, float* out, int32_t channels, int32_t height, int32_t width,
                      void* cuda_stream);

@@ -598,6 +598,27 @@ def test_rays_from_the_reference_matmul_are_exact_at_every_size():
     assert rel_norm_err(a, b) < VOL_TOL
 
 
+@pytest.mark.parametrize("h,w", [(128, 160), (344, 232), (688, 464), (1376, 928), (2752, 1856), (43, 29)])
+def test_rays_for_skips_the_matmul_only_where_the_kernel_order_is_the_reference_order(h, w):
+    """sweep.rays_for decides per image size whether the sweeps may form rot @ [x,y,1] themselves.  The verdict is
+    taken on a probe rotation and the first pose; it must then hold for poses it has never seen (the rounding
+    order is a property of the cuBLAS kernel chosen for the shape, not of the values)."""
+    rig = synth.make_rig(num_views=5)
+    pose_a = sweep.relative_poses(torch.from_numpy(rig.proj(4)).to(DEV))
+    got = sweep.rays_for(pose_a, h, w)
+    if got is not None:
+        assert torch.equal(got, sweep.reference_rays(pose_a, h, w))
+        assert sweep._RAY_ORDER[(h, w, pose_a.device.index)] is False
+        return
+    g = torch.Generator().manual_seed(h * 7 + w)
+    for scale in (1.0, 2.0):
+        fresh = pose_a.clone()
+        fresh[:, :3, :3] += 0.03 * torch.randn(4, 3, 3, generator=g).to(DEV)
+        fresh[:, :2, :] /= scale
+        assert torch.equal(sweep.kernel_rays(fresh, h, w), sweep.reference_rays(fresh, h, w))
+    assert sweep.rays_for(fresh, h, w) is None
+
+
 def test_view_pipeline_matches_direct_calls():
     """pipeline.ViewPipeline (pinned host in, pinned host out, two slots, copy + compute streams): five views through
     two slots give what the synchronous calls give, bit for bit."""
