@@ -9,6 +9,13 @@ Layers (bottom up):
     depthnets        the reference's DepthNet / InferDepthNet forward passes
     shard            reference-view sharding across the GPUs of a node (no collective on the path)
     install()        rebinds the names above inside the reference's own modules (drop-in)
+
+Either side of the path:
+    graphs           the per-plane regulariser + streaming soft-argmax loops as CUDA graphs
+    formats, dataset the workspace text files, PFM / camera files and the MVSDataset tensors (host-side, as upstream)
+    predict, mvs_dl  predict.py's command line and mvs_dl.MVS_Inference on this engine
+    fusion           ConsistencyChecker / fuse_view: the depth-map fusion consistency check (d3d_consistency_fuse)
+    feature_cache    FeatureNet pyramids shared across reference views
 """
 from __future__ import annotations
 
