@@ -66,7 +66,7 @@ REGRESS_MAX_PLANES = 16
 class FuseArgs(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32), ("num_src", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
-        ("src_height", C.c_int32), ("src_width", C.c_int32), ("min_consistent", C.c_int32), ("reserved0", C.c_int32),
+        ("src_height", C.c_int32), ("src_width", C.c_int32), ("min_consistent", C.c_int32), ("accumulate", C.c_int32),
         ("position_threshold", C.c_double),
         ("depth_threshold", C.c_float), ("confidence_threshold", C.c_float), ("normal_threshold_cos", C.c_float),
         ("reserved1", C.c_int32),
@@ -75,7 +75,7 @@ class FuseArgs(C.Structure):
         ("depth_src_out", C.c_void_p * FUSE_MAX_SRC),
         ("mask", C.c_void_p), ("depth_reprojected", _f32p), ("xyz_world_src", _f32p), ("angle_conf", _f32p),
         ("consistent_count", C.c_void_p), ("xyz_fused", _f32p), ("final_mask", C.c_void_p),
-        ("depth_ref_filtered", _f32p),
+        ("depth_ref_filtered", _f32p), ("accum", _f32p),
     ]
 
 

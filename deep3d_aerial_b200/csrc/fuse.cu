@@ -32,6 +32,8 @@ struct FuseParams {
     float* __restrict__ xyz_fused;
     uint8_t* __restrict__ final_mask;
     float* __restrict__ depth_ref_filtered;
+    float* __restrict__ accum;
+    int accumulate;
     double dist2_limit;               // see dist2_limit_of
     float depth_threshold, confidence_threshold, normal_threshold_cos;
     int S, H, W, Hs, Ws, min_consistent;
@@ -114,6 +116,10 @@ __global__ void __launch_bounds__(kFuseThreads) consistency_fuse_kernel(const Fu
           az = (float)row4(G0 + kD + 8, px, py, pz, 1.0);
     float aconf = 1.f;
     int count = 1;
+    if (kFused && p.accumulate) {                          // continue an earlier call over other source views
+        ax = p.accum[pix]; ay = p.accum[hw + pix]; az = p.accum[2 * hw + pix]; aconf = p.accum[3 * hw + pix];
+        count = p.consistent_count[pix];
+    }
     const bool gate = prob > p.confidence_threshold && d > 0.f;
 
     for (int s = 0; s < p.S; ++s) {
@@ -190,6 +196,9 @@ __global__ void __launch_bounds__(kFuseThreads) consistency_fuse_kernel(const Fu
         }
     }
     if (!kFused) return;
+    if (p.accum) {
+        p.accum[pix] = ax; p.accum[hw + pix] = ay; p.accum[2 * hw + pix] = az; p.accum[3 * hw + pix] = aconf;
+    }
     const bool keep = count >= p.min_consistent;
     if (p.consistent_count) p.consistent_count[pix] = count;
     if (p.final_mask) p.final_mask[pix] = keep;
@@ -234,6 +243,8 @@ extern "C" int d3d_consistency_fuse(const D3dFuseArgs* a, void* cuda_stream) {
             return fail(D3D_ERR_BAD_ARGUMENT, "d3d_consistency_fuse: depth_src_out[%d] aliases depth_src[%d] (the gathers "
                         "of one pixel would race with the zeroing of another)", s, s);
     }
+    if (a->accumulate && (!a->accum || !a->consistent_count))
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_consistency_fuse: accumulate needs accum and consistent_count");
     const long long hw = (long long)a->height * a->width;
     if (hw > (1LL << 31) - kFuseThreads) return fail(D3D_ERR_UNSUPPORTED, "d3d_consistency_fuse: H*W too large");
 
@@ -254,6 +265,7 @@ extern "C" int d3d_consistency_fuse(const D3dFuseArgs* a, void* cuda_stream) {
     p.mask = a->mask; p.depth_reprojected = a->depth_reprojected; p.xyz_world_src = a->xyz_world_src;
     p.angle_conf = a->angle_conf; p.consistent_count = a->consistent_count; p.xyz_fused = a->xyz_fused;
     p.final_mask = a->final_mask; p.depth_ref_filtered = a->depth_ref_filtered;
+    p.accum = a->accum; p.accumulate = a->accumulate != 0;
     p.dist2_limit = dist2_limit_of(a->position_threshold);
     p.depth_threshold = a->depth_threshold; p.confidence_threshold = a->confidence_threshold;
     p.normal_threshold_cos = a->normal_threshold_cos;
@@ -263,7 +275,7 @@ extern "C" int d3d_consistency_fuse(const D3dFuseArgs* a, void* cuda_stream) {
     const unsigned blocks = (unsigned)((hw + kFuseThreads - 1) / kFuseThreads);
     const size_t smem = (size_t)(1 + a->num_src) * (kGeom * sizeof(double) + 12 * sizeof(float));
     const bool per_source = p.depth_reprojected || p.angle_conf || p.xyz_world_src;
-    const bool fused = p.consistent_count || p.final_mask || p.depth_ref_filtered || p.xyz_fused;
+    const bool fused = p.consistent_count || p.final_mask || p.depth_ref_filtered || p.xyz_fused || p.accum;
     if (per_source && fused) consistency_fuse_kernel<true, true><<<blocks, kFuseThreads, smem, stream>>>(p);
     else if (per_source) consistency_fuse_kernel<true, false><<<blocks, kFuseThreads, smem, stream>>>(p);
     else consistency_fuse_kernel<false, true><<<blocks, kFuseThreads, smem, stream>>>(p);

@@ -208,7 +208,11 @@ typedef struct D3dFuseArgs {
     int32_t height, width;        /* reference maps                                                   */
     int32_t src_height, src_width;/* source maps (the reference assumes the same extent)              */
     int32_t min_consistent;       /* final_mask = 1 + #consistent sources >= this (fusion_3d_normal.py:536) */
-    int32_t reserved0;
+    int32_t accumulate;           /* 0: the accumulators start from the reference pixel itself (count 1, its world
+                                     point, confidence 1: fusion_3d_normal.py:449-455, 466); 1: they continue from
+                                     `accum` and `consistent_count` as an earlier call over OTHER source views of the
+                                     same reference view left them (a view list that names a source twice must see
+                                     the map the first visit modified, so it is split into several calls)          */
     double position_threshold;    /* pixels, compared in fp64                                         */
     float depth_threshold;        /* relative, compared in fp32                                       */
     float confidence_threshold;   /* on prob_ref, fp32                                                */
@@ -232,6 +236,8 @@ typedef struct D3dFuseArgs {
     float* xyz_fused;             /* [3,H,W] (xyz_ref + sum_s conf_s xyz_s) / (1 + sum_s conf_s)      */
     uint8_t* final_mask;          /* [H,W]                                                            */
     float* depth_ref_filtered;    /* [H,W] depth_ref where final_mask, else 0 (fusion_3d_normal.py:541) */
+    float* accum;                 /* [4,H,W] running sum_s conf_s x, y, z and sum_s conf_s (incl. the reference
+                                     pixel's own point at confidence 1): written when not NULL, read when `accumulate` */
 } D3dFuseArgs;
 
 int d3d_consistency_fuse(const D3dFuseArgs* args, void* cuda_stream);
