@@ -64,7 +64,7 @@ def _dev(t, name, dtype=torch.float32):
 
 def fuse_view(depth_ref, normal_ref, prob_ref, geometry, depth_src, normal_src, *, position_threshold=1.0,
               depth_threshold=0.01, normal_threshold_cos=0.0, confidence_threshold=0.2, min_consistent=4,
-              per_source=False, update_sources=True, out: Optional[dict] = None) -> dict:
+              per_source=False, update_sources=True, accumulate=False, out: Optional[dict] = None) -> dict:
     """One reference view against S <= 16 source views, one kernel launch on the current stream.
 
     depth_ref [H,W], normal_ref [H,W,3], prob_ref [H,W]; depth_src / normal_src: lists of S tensors [Hs,Ws] /
@@ -72,7 +72,8 @@ def fuse_view(depth_ref, normal_ref, prob_ref, geometry, depth_src, normal_src, 
       count [H,W] int32, xyz [3,H,W], final_mask [H,W] bool, depth_ref_filtered [H,W], masks [S,H,W] bool,
       depth_src_out (list of S maps with the consumed pixels zeroed; `update_sources=False` skips them) and, with
       `per_source`, depth_reprojected [S,H,W], xyz_world_src [S,3,H,W], angle_conf [S,H,W].
-    `out` may carry preallocated tensors under the same keys."""
+    `out` may carry preallocated tensors under the same keys.  `accumulate=True` continues the accumulators
+    (`out["accum"]` [4,H,W] and `out["count"]`) an earlier call over OTHER sources of this reference view left."""
     lib = _lib.load()
     s_n = len(depth_src)
     if not 1 <= s_n <= MAX_SRC or len(normal_src) != s_n:
@@ -117,12 +118,74 @@ def fuse_view(depth_ref, normal_ref, prob_ref, geometry, depth_src, normal_src, 
     a.xyz_fused = buf("xyz", (3, h, w), torch.float32).data_ptr()
     a.final_mask = buf("final_mask", (h, w), torch.bool).data_ptr()
     a.depth_ref_filtered = buf("depth_ref_filtered", (h, w), torch.float32).data_ptr()
+    if accumulate or "accum" in out:
+        if accumulate and ("accum" not in out or "count" not in (out or {})):
+            raise ValueError("accumulate=True needs out['accum'] and out['count'] from the earlier call")
+        a.accum = buf("accum", (4, h, w), torch.float32).data_ptr()
+        a.accumulate = int(bool(accumulate))
     if per_source:
         a.depth_reprojected = buf("depth_reprojected", (s_n, h, w), torch.float32).data_ptr()
         a.xyz_world_src = buf("xyz_world_src", (s_n, 3, h, w), torch.float32).data_ptr()
         a.angle_conf = buf("angle_conf", (s_n, h, w), torch.float32).data_ptr()
     _lib.check(lib.d3d_consistency_fuse(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
     return out
+
+
+def fuse_block(view_list, depths, normals, confidences, intrinsics, extrinsics, *, fusion_num=10,
+               position_threshold=1.0, depth_threshold=0.01, normal_threshold=10.0, confidence_threshold=0.2,
+               min_consistent=4, on_view=None):
+    """The reference-view loop of `Fuse_Depth_Map.fuse_depths` (fuse/fusion_3d_normal.py:405-543) with every map
+    resident in HBM instead of travelling through `tmp/*_init.pfm` between reference views.
+
+    view_list: [{"ref": id, "src": [ids...]}, ...] in fusion order (blocks.txt / viewpair.txt);
+    depths, normals, confidences: dict id -> CUDA tensor [H,W] / [H,W,3] / [H,W]; intrinsics, extrinsics: dict id ->
+    numpy K [3,3] / Tcw [4,4].  `depths` IS MODIFIED as upstream modifies its tmp files: after a reference view, each of
+    its sources keeps only the pixels that view did not consume (:519-523) and the reference view itself only its
+    final-mask pixels (:539-543) -- so later views see earlier views' deletions.  A source named twice in one list
+    (the reader pads short lists with the first source, :243-246) is visited again against the map its first visit
+    left, in a follow-up launch that continues the accumulators.
+    Returns {ref id: dict(count, xyz, final_mask, masks [S,H,W], sources [ids])}; `on_view(ref, result)` is called
+    per view if given (results are fresh tensors)."""
+    cos = math.cos(math.radians(normal_threshold))
+    results = {}
+    for pair in view_list:
+        ref = pair["ref"]
+        if ref not in depths:
+            continue                                         # upstream warns and skips (:413-415)
+        srcs = [s for s in pair["src"][:fusion_num] if s in depths]
+        dev = depths[ref].device
+        out, masks, first = {}, [], True
+        at = 0
+        while at < len(srcs) or first:
+            run = []
+            while at < len(srcs) and srcs[at] not in run and len(run) < MAX_SRC:
+                run.append(srcs[at])
+                at += 1
+            if not run:                                      # no source at all: the reference pixel alone
+                break
+            geom = torch.from_numpy(pair_geometry(intrinsics[ref], extrinsics[ref], [intrinsics[s] for s in run],
+                                                  [extrinsics[s] for s in run])).to(dev)
+            keep = {k: out[k] for k in ("accum", "count") if k in out}
+            if first:
+                keep["accum"] = torch.empty((4,) + tuple(depths[ref].shape), device=dev, dtype=torch.float32)
+            out = fuse_view(depths[ref], normals[ref], confidences[ref], geom, [depths[s] for s in run],
+                            [normals[s] for s in run], position_threshold=position_threshold,
+                            depth_threshold=depth_threshold, normal_threshold_cos=cos,
+                            confidence_threshold=confidence_threshold, min_consistent=min_consistent,
+                            accumulate=not first, out=keep)
+            for s, new in zip(run, out["depth_src_out"]):
+                depths[s] = new                              # tmp/<src>_init.pfm
+            masks.append(out["masks"])
+            first = False
+        if first:                                            # empty source list
+            continue
+        depths[ref] = out["depth_ref_filtered"]              # tmp/<ref>_init.pfm
+        res = {"count": out["count"], "xyz": out["xyz"], "final_mask": out["final_mask"],
+               "masks": torch.cat(masks, 0), "sources": srcs}
+        results[ref] = res
+        if on_view is not None:
+            on_view(ref, res)
+    return results
 
 
 class ConsistencyChecker(object):

@@ -112,3 +112,47 @@ def fuse_view(depth_ref, normal_ref, intrinsics_ref, extrinsics_ref, prob_map_re
     filtered[~final] = 0                                                        # :541-543
     return {"count": count, "xyz": xyz, "final_mask": final, "depth_ref_filtered": filtered,
             "masks": np.stack(masks), "depth_src_out": outs}
+
+
+def fuse_block(view_list, depths, normals, confidences, intrinsics, extrinsics, fusion_num=10, min_consistent=4, **th):
+    """The reference-view loop of `fuse_depths` (fusion_3d_normal.py:405-543) with the tmp/*_init.pfm files kept in a
+    dict: a source's map is replaced by what `check` returns (:519-523), the reference view's by its final-mask
+    pixels (:539-543), and every later read takes the replaced map (:409-411, 475-477).  `depths` is modified.
+    No live run of the reference stands behind this loop (that file needs IO.*, tools.*, matplotlib and a parsed
+    command line to import): parity unpinned for the loop, pinned for `check`."""
+    results = {}
+    for pair in view_list:
+        ref = pair["ref"]
+        if ref not in depths:
+            continue
+        d_ref, n_ref, prob = depths[ref], normals[ref], confidences[ref]
+        k_ref, e_ref = intrinsics[ref], extrinsics[ref]
+        height, width = d_ref.shape
+        x_ref, y_ref = np.meshgrid(np.arange(0, width), np.arange(0, height))
+        xr, yr = x_ref.reshape([-1]), y_ref.reshape([-1])
+        cam = np.matmul(np.linalg.inv(k_ref), np.vstack((xr, yr, np.ones_like(xr))) * d_ref.reshape([-1]))
+        world = np.matmul(np.linalg.inv(e_ref), np.vstack((cam, np.ones_like(xr))))[:3]
+        all_xyz = world.reshape([-1, height, width]).astype(np.float32)
+        conf_sum = 0 + np.ones_like(all_xyz)
+        count = 0 + np.ones([height, width], dtype=np.int32)
+        masks, used = [], []
+        for src in pair["src"][:fusion_num]:
+            if src not in depths:
+                continue
+            mask, _, removed, xyz_src, angle = check(d_ref, n_ref, k_ref, e_ref, depths[src], normals[src],
+                                                     intrinsics[src], extrinsics[src], prob, **th)
+            depths[src] = removed
+            count = count + mask.astype(np.int32)
+            all_xyz += (angle * xyz_src).astype(np.float32)
+            conf_sum = conf_sum + angle
+            masks.append(mask)
+            used.append(src)
+        if not used:
+            continue
+        final = np.array(count >= min_consistent)
+        filtered = np.array(d_ref)
+        filtered[~final] = 0
+        depths[ref] = filtered
+        results[ref] = {"count": count, "xyz": (all_xyz / conf_sum).astype(np.float32), "final_mask": final,
+                        "masks": np.stack(masks), "sources": used}
+    return results

@@ -209,3 +209,59 @@ def test_full_size_properties():
     dref, nref, k, e, prob = sc["ref"]
     sub = fuse_np.fuse_view(dref[:rows], nref[:rows], k, e, prob[:rows], sc["src"][:3], min_consistent=2, **TH)
     assert np.array_equal(masks[:3, :rows].cpu().numpy(), sub["masks"])
+
+
+def _block_inputs(seed=3, h=40, w=48):
+    sc = synth.fusion_scene(num_src=3, height=h, width=w, seed=seed)
+    views = [sc["ref"][:4]] + sc["src"]
+    rng = np.random.default_rng(seed)
+    depths = {i: v[0].copy() for i, v in enumerate(views)}
+    normals = {i: v[1] for i, v in enumerate(views)}
+    conf = {i: rng.random((h, w)).astype(np.float32) for i in range(4)}
+    return depths, normals, conf, {i: v[2] for i, v in enumerate(views)}, {i: v[3] for i, v in enumerate(views)}
+
+
+VIEW_LIST = [{"ref": 0, "src": [1, 2, 3, 1, 1]},      # a padded list: source 1 three times (fusion_3d_normal.py:243-246)
+             {"ref": 1, "src": [0, 2]},               # sees what view 0 left of maps 0 and 2
+             {"ref": 7, "src": [0]},                  # no depth map for this view: skipped
+             {"ref": 2, "src": [9]},                  # no usable source: skipped
+             {"ref": 3, "src": [0, 1, 2]}]
+
+
+def test_oracle_block_loop_carries_the_consumed_maps():
+    depths, normals, conf, K, E = _block_inputs()
+    before = {k: v.copy() for k, v in depths.items()}
+    r = fuse_np.fuse_block(VIEW_LIST, depths, normals, conf, K, E, min_consistent=2, **TH)
+    assert sorted(r) == [0, 1, 3] and r[0]["masks"].shape[0] == 5 and r[0]["sources"] == [1, 2, 3, 1, 1]
+    assert not (r[0]["masks"][0] & r[0]["masks"][3] & (before[1] == 0)).any()
+    # a second visit of source 1 cannot re-use pixels the first visit consumed
+    first, second = r[0]["masks"][0], r[0]["masks"][3]
+    assert second.sum() < first.sum()
+    for k in depths:
+        changed = depths[k] != before[k]
+        assert (depths[k][changed] == 0).all()
+    assert (depths[0] == 0).sum() > (before[0] == 0).sum()
+
+
+@pytest.mark.gpu
+def test_fuse_block_matches_the_oracle_loop_including_repeated_sources():
+    depths, normals, conf, K, E = _block_inputs()
+    want_depths = {k: v.copy() for k, v in depths.items()}
+    want = fuse_np.fuse_block(VIEW_LIST, want_depths, normals, conf, K, E, min_consistent=2, **TH)
+    dev = torch.device("cuda", 0)
+    up = lambda d: {k: torch.from_numpy(v).to(dev) for k, v in d.items()}          # noqa: E731
+    got_depths = up(depths)
+    seen = []
+    got = fusion.fuse_block(VIEW_LIST, got_depths, up(normals), up(conf), K, E, min_consistent=2,
+                            position_threshold=TH["position_threshold"], depth_threshold=TH["depth_threshold"],
+                            normal_threshold=10.0, confidence_threshold=TH["confidence_threshold"],
+                            on_view=lambda ref, res: seen.append(ref))
+    assert seen == [0, 1, 3] and sorted(got) == sorted(want)
+    for ref in want:
+        assert got[ref]["sources"] == want[ref]["sources"]
+        assert np.array_equal(got[ref]["masks"].cpu().numpy(), want[ref]["masks"]), ref
+        assert np.array_equal(got[ref]["count"].cpu().numpy(), want[ref]["count"]), ref
+        assert np.array_equal(got[ref]["final_mask"].cpu().numpy(), want[ref]["final_mask"]), ref
+        assert _close(got[ref]["xyz"].cpu().numpy(), want[ref]["xyz"], float(np.abs(want[ref]["xyz"]).max())), ref
+    for k in want_depths:                                   # the state the next scene block would start from
+        assert np.array_equal(got_depths[k].cpu().numpy(), want_depths[k]), k
