@@ -131,6 +131,65 @@ def fuse_view(depth_ref, normal_ref, prob_ref, geometry, depth_src, normal_src, 
     return out
 
 
+def read_camera_parameters(filename, scale=1.0, cams_ori="XrightYdown", images_ori="Tcw"):
+    """`<name>.txt` as `predict.py` writes it -> (K [3,3] float32, Tcw [4,4] float32, image path), parsed as
+    `Fuse_Depth_Map.read_camera_parameters` / `create_extrinsics_matrix` parse it (fusion_3d_normal.py:112-172):
+    float32 throughout, rows 0-1 of K times `scale`, and for the default 'Tcw' orientation the extrinsics go
+    through inverse, axis flip, inverse -- in float32, which changes their low bits, so it is restated as is."""
+    with open(filename) as f:
+        lines = [line.rstrip() for line in f.readlines()]
+    extr = np.array(" ".join(lines[1:5]).split(), dtype=np.float32).reshape((4, 4))
+    flip = np.eye(3, dtype=np.float32)
+    if cams_ori == "XrightYup":
+        flip[1, 1] = flip[2, 2] = -1
+    if images_ori == "Twc":
+        extr[0:3, 0:3] = np.matmul(extr[0:3, 0:3], flip)
+        extr = np.linalg.inv(extr)
+    elif images_ori == "Rcw":
+        extr[0:3, 0:3] = np.linalg.inv(np.matmul(flip, extr[0:3, 0:3]))
+        extr = np.linalg.inv(extr)
+    elif images_ori == "Tcw":
+        extr = np.linalg.inv(extr)
+        extr[0:3, 0:3] = np.matmul(extr[0:3, 0:3], flip)
+        extr = np.linalg.inv(extr)
+    intr = np.array(" ".join(lines[7:10]).split(), dtype=np.float32).reshape((3, 3))
+    intr[:2, :] *= scale
+    image_path = lines[13].split(" ")[4]
+    return intr, extr, image_path
+
+
+def load_mvs_outputs(depth_path, names, device, camera_scale=1.0):
+    """What `fuse_depths` reads per view from the MVS output folder (fusion_3d_normal.py:405-440, 470-489), as the
+    dicts `fuse_block` takes: `<name>_init.pfm`, `<name>_prob.pfm` (ones if missing), `<name>_normal.pfm` mapped from
+    [0,1] to [-1,1] (`read_normal`; missing: the default normal (0,0,-1)), `<name>.txt`.  Views without a depth map
+    are left out (upstream warns and skips them)."""
+    import os
+
+    from .formats import load_pfm_utf8
+
+    depths, normals, confs, intr, extr = {}, {}, {}, {}, {}
+    for name in names:
+        base = os.path.join(depth_path, str(name))
+        if not os.path.exists(base + "_init.pfm"):
+            continue
+        depth = np.ascontiguousarray(load_pfm_utf8(base + "_init.pfm")[0], dtype=np.float32)
+        h, w = depth.shape
+        if os.path.exists(base + "_normal.pfm"):
+            normal = np.ascontiguousarray(load_pfm_utf8(base + "_normal.pfm")[0] * 2.0 - 1.0, dtype=np.float32)
+        else:
+            normal = np.zeros([h, w, 3], dtype=np.float32)
+            normal[:, :, 2] = -1.0
+        if os.path.exists(base + "_prob.pfm"):
+            conf = np.ascontiguousarray(load_pfm_utf8(base + "_prob.pfm")[0], dtype=np.float32)
+        else:
+            conf = np.ones([h, w], dtype=np.float32)
+        intr[name], extr[name], _ = read_camera_parameters(base + ".txt", camera_scale)
+        depths[name] = torch.from_numpy(depth).to(device)
+        normals[name] = torch.from_numpy(normal).to(device)
+        confs[name] = torch.from_numpy(conf).to(device)
+    return depths, normals, confs, intr, extr
+
+
 def fuse_block(view_list, depths, normals, confidences, intrinsics, extrinsics, *, fusion_num=10,
                position_threshold=1.0, depth_threshold=0.01, normal_threshold=10.0, confidence_threshold=0.2,
                min_consistent=4, on_view=None):

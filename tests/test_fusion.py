@@ -265,3 +265,26 @@ def test_fuse_block_matches_the_oracle_loop_including_repeated_sources():
         assert _close(got[ref]["xyz"].cpu().numpy(), want[ref]["xyz"], float(np.abs(want[ref]["xyz"]).max())), ref
     for k in want_depths:                                   # the state the next scene block would start from
         assert np.array_equal(got_depths[k].cpu().numpy(), want_depths[k]), k
+
+
+def test_camera_files_are_parsed_as_the_fusion_stage_parses_them(tmp_path):
+    """`<name>.txt` written by the MVS stage (formats.write_red_cam) read back the way fusion_3d_normal.py:112-172 does:
+    float32, and the default 'Tcw' orientation runs the extrinsics through two float32 inversions."""
+    from deep3d_aerial_b200 import formats
+    sc = synth.fusion_scene(num_src=1, height=8, width=8, seed=0)
+    _, _, k, e, _ = sc["ref"]
+    cam = np.zeros((2, 4, 4), dtype=np.float32)
+    cam[0], cam[1, :3, :3], cam[1, 3] = e, k, [400.0, 0.5, 384, 640.0]
+    p = str(tmp_path / "v.txt")
+    formats.write_red_cam(p, cam, ["8", "8", "3", "v.png"], "/data/images/v.png")
+    intr, extr, path = fusion.read_camera_parameters(p, scale=0.5)
+    want_k = k.copy()
+    want_k[:2] *= 0.5
+    assert intr.dtype == np.float32 and np.array_equal(intr, want_k) and path == "/data/images/v.png"
+    want_e = np.linalg.inv(np.linalg.inv(e))                       # float32 both times (create_extrinsics_matrix, 'Tcw')
+    assert extr.dtype == np.float32 and np.array_equal(extr, want_e)
+    up = fusion.read_camera_parameters(p, cams_ori="XrightYup")[1]
+    flip = np.diag([1.0, -1.0, -1.0, 1.0]).astype(np.float32)             # Tcw of a y-up camera: rows 1, 2 change sign
+    assert np.allclose(up, flip @ e, rtol=1e-4, atol=1e-2)
+    twc = fusion.read_camera_parameters(p, images_ori="Twc")[1]
+    assert np.allclose(twc, np.linalg.inv(e), atol=1e-3)
