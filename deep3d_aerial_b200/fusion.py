@@ -247,6 +247,72 @@ def fuse_block(view_list, depths, normals, confidences, intrinsics, extrinsics, 
     return results
 
 
+class FusionPipeline:
+    """Reference views streamed from pinned host memory against source maps that stay in HBM: the upload of view
+    n+1 and the download of view n-1 overlap the kernel of view n (three streams, two slots; PCIe carries both
+    directions at once).  `submit` takes pinned CPU tensors depth [H,W], normal [H,W,3], prob [H,W] and the
+    `pair_geometry` block (numpy or pinned tensor); `collect` returns the oldest submitted view's
+    {"count", "xyz", "final_mask", "depth_ref_filtered"} as pinned CPU tensors (valid until two more submits)."""
+
+    KEYS = ("count", "xyz", "final_mask", "depth_ref_filtered")
+
+    def __init__(self, height, width, num_src, device, slots=2, **thresholds):
+        self.dev = torch.device(device)
+        self.th = thresholds
+        self.streams = [torch.cuda.Stream(self.dev) for _ in range(3)]            # up, compute, down
+        self.slots = []
+        shapes = {"depth": (height, width), "normal": (height, width, 3), "prob": (height, width)}
+        for _ in range(slots):
+            s = {k: torch.empty(v, device=self.dev) for k, v in shapes.items()}
+            s["geom"] = torch.empty((1 + num_src, _lib.FUSE_GEOM_DOUBLES), device=self.dev, dtype=torch.float64)
+            s["geom_host"] = torch.empty((1 + num_src, _lib.FUSE_GEOM_DOUBLES), dtype=torch.float64).pin_memory()
+            s["out"] = {}
+            s["host"] = None
+            for name in ("copied", "done", "downloaded"):
+                s[name] = torch.cuda.Event()
+                s[name].record(torch.cuda.current_stream(self.dev))
+            self.slots.append(s)
+        self.pending = []
+        self._next = 0
+
+    def submit(self, depth_ref, normal_ref, prob_ref, geometry, depth_src, normal_src):
+        s = self.slots[self._next]
+        self._next = (self._next + 1) % len(self.slots)
+        up, compute, down = self.streams
+        if isinstance(geometry, np.ndarray):
+            s["geom_host"].copy_(torch.from_numpy(geometry))
+            geometry = s["geom_host"]
+        with torch.cuda.stream(up):
+            up.wait_event(s["done"])                          # the slot's previous kernel has read its inputs
+            s["depth"].copy_(depth_ref, non_blocking=True)
+            s["normal"].copy_(normal_ref, non_blocking=True)
+            s["prob"].copy_(prob_ref, non_blocking=True)
+            s["geom"].copy_(geometry, non_blocking=True)
+            s["copied"].record()
+        with torch.cuda.stream(compute):
+            compute.wait_event(s["copied"])
+            compute.wait_event(s["downloaded"])               # the slot's previous results have left
+            s["out"] = fuse_view(s["depth"], s["normal"], s["prob"], s["geom"], depth_src, normal_src, out=s["out"],
+                                 **self.th)
+            s["done"].record()
+        with torch.cuda.stream(down):
+            down.wait_event(s["done"])
+            if s["host"] is None:
+                s["host"] = {k: torch.empty(s["out"][k].shape, dtype=s["out"][k].dtype).pin_memory() for k in self.KEYS}
+            for k in self.KEYS:
+                s["host"][k].copy_(s["out"][k], non_blocking=True)
+            s["downloaded"].record()
+        self.pending.append(s)
+
+    def collect(self):
+        s = self.pending.pop(0)
+        s["downloaded"].synchronize()
+        return s["host"]
+
+    def drain(self):
+        return [self.collect() for _ in range(len(self.pending))]
+
+
 class ConsistencyChecker(object):
     """Drop-in for `fuse/consistency_check_n.py:ConsistencyChecker`: same constructor, same `check` signature,
     numpy arrays in and out.  `implement` is accepted for compatibility (upstream asserts it is one of

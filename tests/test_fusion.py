@@ -288,3 +288,33 @@ def test_camera_files_are_parsed_as_the_fusion_stage_parses_them(tmp_path):
     assert np.allclose(up, flip @ e, rtol=1e-4, atol=1e-2)
     twc = fusion.read_camera_parameters(p, images_ori="Twc")[1]
     assert np.allclose(twc, np.linalg.inv(e), atol=1e-3)
+
+
+@pytest.mark.gpu
+def test_fusion_pipeline_matches_direct_calls():
+    """Overlapped uploads / kernel / downloads give the bytes the direct call gives, view after view, slot reuse included."""
+    dev = torch.device("cuda", 0)
+    scenes = [synth.fusion_scene(num_src=3, height=48, width=64, seed=20 + i) for i in range(5)]
+    src_d = [torch.from_numpy(v[0]).to(dev) for v in scenes[0]["src"]]
+    src_n = [torch.from_numpy(v[1]).to(dev) for v in scenes[0]["src"]]
+    th = dict(position_threshold=1.0, depth_threshold=0.01, normal_threshold_cos=TH["normal_cos"],
+              confidence_threshold=0.2, min_consistent=2)
+    pipe = fusion.FusionPipeline(48, 64, 3, dev, **th)
+    got = []
+    for i, sc in enumerate(scenes):
+        d, n, k, e, prob = sc["ref"]
+        geom = fusion.pair_geometry(k, e, [v[2] for v in scenes[0]["src"]], [v[3] for v in scenes[0]["src"]])
+        pipe.submit(torch.from_numpy(d).pin_memory(), torch.from_numpy(n).pin_memory(), torch.from_numpy(prob).pin_memory(),
+                    geom, src_d, src_n)
+        if i >= 1:
+            got.append({k_: v.clone() for k_, v in pipe.collect().items()})
+    got += [{k_: v.clone() for k_, v in r.items()} for r in pipe.drain()]
+    assert len(got) == 5
+    for sc, g in zip(scenes, got):
+        d, n, k, e, prob = sc["ref"]
+        geom = torch.from_numpy(fusion.pair_geometry(k, e, [v[2] for v in scenes[0]["src"]],
+                                                     [v[3] for v in scenes[0]["src"]])).to(dev)
+        want = fusion.fuse_view(torch.from_numpy(d).to(dev), torch.from_numpy(n).to(dev), torch.from_numpy(prob).to(dev),
+                                geom, src_d, src_n, **th)
+        for key in fusion.FusionPipeline.KEYS:
+            assert torch.equal(g[key], want[key].cpu()), key
