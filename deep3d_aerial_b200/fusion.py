@@ -280,6 +280,7 @@ class FusionPipeline:
         self._next = (self._next + 1) % len(self.slots)
         up, compute, down = self.streams
         if isinstance(geometry, np.ndarray):
+            s["copied"].synchronize()                         # the slot's previous upload has left its pinned block
             s["geom_host"].copy_(torch.from_numpy(geometry))
             geometry = s["geom_host"]
         with torch.cuda.stream(up):
