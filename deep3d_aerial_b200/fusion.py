@@ -277,6 +277,9 @@ class FusionPipeline:
 
     def submit(self, depth_ref, normal_ref, prob_ref, geometry, depth_src, normal_src):
         s = self.slots[self._next]
+        if any(s is q for q in self.pending):
+            raise RuntimeError("FusionPipeline: collect() the view submitted %d calls ago before submitting another "
+                               "(its slot would be overwritten)" % len(self.slots))
         self._next = (self._next + 1) % len(self.slots)
         up, compute, down = self.streams
         if isinstance(geometry, np.ndarray):

@@ -310,6 +310,13 @@ def test_fusion_pipeline_matches_direct_calls():
             got.append({k_: v.clone() for k_, v in pipe.collect().items()})
     got += [{k_: v.clone() for k_, v in r.items()} for r in pipe.drain()]
     assert len(got) == 5
+    for _ in range(2):
+        pipe.submit(torch.from_numpy(d).pin_memory(), torch.from_numpy(n).pin_memory(), torch.from_numpy(prob).pin_memory(),
+                    geom, src_d, src_n)
+    with pytest.raises(RuntimeError, match="collect"):          # both slots hold uncollected views
+        pipe.submit(torch.from_numpy(d).pin_memory(), torch.from_numpy(n).pin_memory(), torch.from_numpy(prob).pin_memory(),
+                    geom, src_d, src_n)
+    pipe.drain()
     for sc, g in zip(scenes, got):
         d, n, k, e, prob = sc["ref"]
         geom = torch.from_numpy(fusion.pair_geometry(k, e, [v[2] for v in scenes[0]["src"]],
