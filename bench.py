@@ -716,4 +716,10 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    rc = main()
+    try:
+        from deep3d_aerial_b200 import shard as _shard
+        _shard.finalize()
+    except Exception:  # noqa: BLE001 -- teardown only
+        pass
+    sys.exit(rc)

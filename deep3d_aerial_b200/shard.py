@@ -69,8 +69,16 @@ def init(backend: Optional[str] = None) -> tuple:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=size)
+            dist.init_process_group(backend=backend, rank=rank, world_size=size, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend=backend, rank=rank, world_size=size)
     return rank, size, local
+
+
+def finalize() -> None:
+    """Tear the process group down (call once, at the end of a rank's work)."""
+    if dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def _device():
