@@ -69,9 +69,9 @@ def init(backend: Optional[str] = None) -> tuple:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-            dist.init_process_group(backend=backend, rank=rank, world_size=size, device_id=torch.device("cuda", local))
-        else:
-            dist.init_process_group(backend=backend, rank=rank, world_size=size)
+        # (no device_id: an eagerly initialised NCCL communicator prints its version banner on STDOUT, next to the
+        # one JSON line bench.py owes its caller)
+        dist.init_process_group(backend=backend, rank=rank, world_size=size)
     return rank, size, local
 
 
