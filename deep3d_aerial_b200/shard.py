@@ -69,8 +69,10 @@ def init(backend: Optional[str] = None) -> tuple:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        # (no device_id: an eagerly initialised NCCL communicator prints its version banner on STDOUT, next to the
-        # one JSON line bench.py owes its caller)
+        # NCCL_DEBUG=VERSION (set on the GPU pool) makes NCCL print its version banner on STDOUT, next to the one JSON
+        # line bench.py owes its caller: demote that level to WARN; any other explicit setting is the user's
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group(backend=backend, rank=rank, world_size=size)
     return rank, size, local
 
