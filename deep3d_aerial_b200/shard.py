@@ -10,6 +10,7 @@ process group was created with (NCCL on the GPU box, gloo in the CPU tests).
 from __future__ import annotations
 
 import os
+import sys
 from typing import List, Optional, Sequence
 
 import torch
@@ -69,11 +70,19 @@ def init(backend: Optional[str] = None) -> tuple:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        # NCCL_DEBUG=VERSION (set on the GPU pool) makes NCCL print its version banner on STDOUT, next to the one JSON
-        # line bench.py owes its caller: demote that level to WARN; any other explicit setting is the user's
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group(backend=backend, rank=rank, world_size=size)
+        # NCCL prints its version banner on STDOUT when the first communicator is created -- next to the one JSON
+        # line bench.py owes its caller.  Create the communicator here, with file descriptor 1 pointed at stderr.
+        sys.stdout.flush()
+        saved = os.dup(1)
+        try:
+            os.dup2(2, 1)
+            dist.init_process_group(backend=backend, rank=rank, world_size=size)
+            if backend == "nccl":
+                dist.barrier()
+                torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     return rank, size, local
 
 
