@@ -10,6 +10,7 @@ inference script, mvs/mvs_cas/predict.py:49).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -119,7 +120,9 @@ def rays_for(pose: torch.Tensor, h: int, w: int) -> Optional[torch.Tensor]:
     on the values: the first call at a size computes both forms, for a generic dense probe rotation AND for the
     pose at hand, and compares them bit for bit (one host sync per size and device, so call it outside CUDA-graph
     capture); every later call at that size reuses the verdict.  At 1856 x 2752 the skipped matmuls are 0.9 ms of
-    a 10.7 ms AdaMVS view."""
+    a 10.7 ms AdaMVS view.  `D3D_RAYS=matmul` in the environment forces the matmul everywhere."""
+    if os.environ.get("D3D_RAYS", "") == "matmul":           # escape hatch: always the reference's own product
+        return reference_rays(pose, h, w)
     key = (h, w, pose.device.index)
     same = _RAY_ORDER.get(key)
     if same is None:
