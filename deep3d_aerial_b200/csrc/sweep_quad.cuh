@@ -54,11 +54,39 @@ struct RefetchTok<NV, TEXB, NV> {
                                                unsigned, int, int, int) {}
 };
 
+// The same in two phases (issue_tok / rebuild_tok): every moved view's loads are started before any view is rebuilt,
+// so their latencies overlap instead of adding up.
+template <int NV, int TEXB, int V = 0>
+struct RefetchIssue {
+    static __device__ __forceinline__ void run(float2 (&tex)[NV][4][2], unsigned (&ckey)[NV], unsigned& mv, const float4 (&g)[NV],
+                                               const float* base, unsigned row_bytes, int hw, int W, int H) {
+        issue_tok<V + 1, TEXB>(tex[V], ckey[V], mv, __float_as_uint(g[V].w), base, row_bytes, hw, W, H);
+        RefetchIssue<NV, TEXB, V + 1>::run(tex, ckey, mv, g, base, row_bytes, hw, W, H);
+    }
+};
+template <int NV, int TEXB>
+struct RefetchIssue<NV, TEXB, NV> {
+    static __device__ __forceinline__ void run(float2 (&)[NV][4][2], unsigned (&)[NV], unsigned&, const float4 (&)[NV],
+                                               const float*, unsigned, int, int, int) {}
+};
+template <int NV, int V = 0>
+struct RefetchRebuild {
+    static __device__ __forceinline__ void run(float2 (&tex)[NV][4][2], unsigned mv) {
+        rebuild_tok<V + 1>(tex[V], mv);
+        RefetchRebuild<NV, V + 1>::run(tex, mv);
+    }
+};
+template <int NV>
+struct RefetchRebuild<NV, NV> {
+    static __device__ __forceinline__ void run(float2 (&)[NV][4][2], unsigned) {}
+};
+
 // MODE: D3D_AGG_VARIANCE, D3D_AGG_WEIGHTED_PRODUCT (both write C rows per plane) or D3D_AGG_GROUP_CORR
 // (p.groups rows; a lane's 4 channels are whole groups, one group, or a slice of a group that spans lanes).
 // D3D_AGG_PAIR_MEAN writes one row per source view (mean over all channels of ref * warped).
 // GS: channels per group known at compile time (4 = the G=8 configuration of BASELINE.json), 0 = read p.groups.
-template <int NV, int MODE, bool kIeeeDiv, bool kPerPix, int GS = 0, int LPP = 8>
+// kSplit: two-phase re-fetch (short sweeps, where most planes re-fetch: cascade stages 1 and 2).
+template <int NV, int MODE, bool kIeeeDiv, bool kPerPix, int GS = 0, int LPP = 8, bool kSplit = false>
 __global__ void __launch_bounds__(256, (NV <= 2 && kQuadThreeCtas) ? 3 : 2) sweep_quad_kernel(const SweepParams p) {
     constexpr int CPT = 4, PPW = 32 / LPP, NP = 2, C = CPT * LPP;
     constexpr int PIX = 8 * PPW;                           // pixels per CTA: 32, 64 or 128
@@ -335,8 +363,15 @@ __global__ void __launch_bounds__(256, (NV <= 2 && kQuadThreeCtas) ? 3 : 2) swee
             unsigned moved = 0;
 #pragma unroll
             for (int v = 0; v < NV; ++v) moved |= __float_as_uint(g[v].w) ^ ckey[v];
-            if (moved)                               // some footprint moved: re-fetch those (in place)
-                RefetchTok<NV, C * 4>::run(tex, ckey, g, feats_c, row_bytes, p.HW, p.W, p.H);
+            if (moved) {                             // some footprint moved: re-fetch those (in place)
+                if constexpr (kSplit) {
+                    unsigned mv = 0;
+                    RefetchIssue<NV, C * 4>::run(tex, ckey, mv, g, feats_c, row_bytes, p.HW, p.W, p.H);
+                    RefetchRebuild<NV>::run(tex, mv);
+                } else {
+                    RefetchTok<NV, C * 4>::run(tex, ckey, g, feats_c, row_bytes, p.HW, p.W, p.H);
+                }
+            }
             float4 ea, eb;
             if (t < JPL) project_chain(t, dnext, ea, eb);    // next pass, interleaved with the arithmetic
 
@@ -453,6 +488,19 @@ int launch_sweep_quad(const SweepParams& p, dim3 grid, cudaStream_t stream, bool
     void (*kern)(const SweepParams);
     const int which = (ieee_div ? 2 : 0) + (p.perpix ? 1 : 0);
     const bool g8 = MODE == D3D_AGG_GROUP_CORR && LPP == 8 && p.groups == 8 && !ieee_div;   // groups of 4 = one lane
+    // two-phase re-fetch for the short sweeps of the cascade (48 / 32 / 8 planes: a footprint lasts 1-3 planes, most
+    // planes re-fetch: -13 % / -10 % on the stage-1 / stage-2 shapes); the one-block form for long sweeps (384 planes,
+    // 9 % re-fetch rate: the two-phase form costs 1 % there).  A/B: variant 18 forces it, variant 32 forbids it.
+    const bool split = !(p.flags & 16) && ((p.flags & 2) != 0 || p.d_end - p.d_begin <= 128) && !ieee_div && !g8;
+    if (split) {
+        kern = p.perpix ? sweep_quad_kernel<NV, MODE, false, true, 0, LPP, true>
+                        : sweep_quad_kernel<NV, MODE, false, false, 0, LPP, true>;
+        static SmemOptIn opted_split[2];
+        if (int rc = opted_split[p.perpix ? 1 : 0].ensure(kern, smem_req)) return rc;
+        kern<<<grid, 256, smem_req, stream>>>(p);
+        count_launch();
+        return check_launch("sweep_quad_kernel");
+    }
     switch (which) {
         case 0: kern = g8 ? sweep_quad_kernel<NV, MODE, false, false, (LPP == 8 ? 4 : 0), LPP>
                           : sweep_quad_kernel<NV, MODE, false, false, 0, LPP>; break;

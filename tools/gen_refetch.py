@@ -313,6 +313,108 @@ __device__ __forceinline__ void refetch_tok(float2 (&t)[4][%d], unsigned& cur_ke
 """ % (cpt // 2, body, outs)
 
 
+def block_tok_split(cpt):
+    """The token-keyed re-fetch in two halves: issue_tok() starts the loads of a moved footprint into the cache
+    registers (raw corners) and records the view in `moved`; rebuild_tok() turns the corners into A, B, C, D.  A
+    caller that issues every view before it rebuilds any has the loads of all views in flight at once -- what the
+    short sweeps of the cascade need, where a footprint lasts 1-3 planes and the re-fetch latency, paid once per
+    view in the one-block form, is half of all stall samples (profiles/ncu_r1_cfg3.txt)."""
+    n = 4 * cpt
+    old, mv, key, base, rowb, hw, wid, hei, wm1, hm1, vplus1, texb, texb16 = (n + i for i in range(13))
+    L = []
+    A = L.append
+    A("{")
+    A(".reg .pred p, q, r, px0, px1, py0, py1;")
+    A(".reg .b32 x0, y0, x1, y1, t;")
+    A(".reg .b64 w, pa, pc;")
+    A("setp.eq.u32 p, %%%d, %%%d;" % (key, old))
+    A("@p bra SAME;")
+    A("mov.u32 %%%d, %%%d;" % (old, key))
+    A("or.b32 %%%d, %%%d, 1 << %%%d;" % (mv, mv, vplus1))
+    A("bfe.s32 x0, %%%d, 0, 16;" % key)
+    A("bfe.s32 y0, %%%d, 16, 16;" % key)
+    A("mad.lo.s32 t, y0, %%%d, x0;" % wid)
+    A("mad.lo.s32 t, %%%d, %%%d, t;" % (hw, vplus1))
+    A("mad.wide.s32 pa, t, %%%d, %%%d;" % (texb, base))
+    A("cvt.u64.u32 w, %%%d;" % rowb)
+    A("add.s64 pc, pa, w;")
+    A("setp.lt.u32 q, x0, %%%d;" % wm1)
+    A("setp.lt.u32 r, y0, %%%d;" % hm1)
+    A("and.pred q, q, r;")
+    A("@!q bra SPECIAL;")
+    for k, (ptr, off) in enumerate([("pa", 0), ("pa", 1), ("pc", 0), ("pc", 1)]):
+        for c in range(0, cpt, 4):
+            b = k * cpt + c
+            if off:
+                o = "+%%%d" % (texb16 if c else texb)
+            else:
+                o = "+16" if c else ""
+            A("ld.global.nc.v4.f32 {%%%d, %%%d, %%%d, %%%d}, [%s%s];" % (b, b + 1, b + 2, b + 3, ptr, o))
+    A("bra SAME;")
+    A("SPECIAL:")
+    A("add.s32 x1, x0, 1;")
+    A("add.s32 y1, y0, 1;")
+    A("setp.lt.u32 px0, x0, %%%d;" % wid)
+    A("setp.lt.u32 px1, x1, %%%d;" % wid)
+    A("setp.lt.u32 py0, y0, %%%d;" % hei)
+    A("setp.lt.u32 py1, y1, %%%d;" % hei)
+    for i in range(n):
+        A("mov.f32 %%%d, 0f00000000;" % i)
+    for k, (ptr, off, pxn, pyn) in enumerate([("pa", 0, "px0", "py0"), ("pa", 1, "px1", "py0"), ("pc", 0, "px0", "py1"), ("pc", 1, "px1", "py1")]):
+        A("and.pred q, %s, %s;" % (pxn, pyn))
+        for c in range(0, cpt, 4):
+            b = k * cpt + c
+            if off:
+                o = "+%%%d" % (texb16 if c else texb)
+            else:
+                o = "+16" if c else ""
+            A("@q ld.global.nc.v4.f32 {%%%d, %%%d, %%%d, %%%d}, [%s%s];" % (b, b + 1, b + 2, b + 3, ptr, o))
+    A("SAME:")
+    A("}")
+    body = "\n        ".join('"%s\\n\\t"' % x for x in L)
+    ops = tex_operands(cpt)
+    ops.append('"+r"(cur_key)')
+    ops.append('"+r"(moved)')
+    outs = ",\n          ".join(", ".join(ops[i:i + 4]) for i in range(0, len(ops), 4))
+    issue = """// Split token-keyed re-fetch, first half (see block_tok_split in tools/gen_refetch.py): when `key` moved, start the
+// loads of the new footprint into the cache registers (raw corners a, b, c, d; corners outside the image = 0), update
+// `cur_key` and set bit VPLUS1 of `moved`.
+template <int VPLUS1, int TEXEL_BYTES>
+__device__ __forceinline__ void issue_tok(float2 (&t)[4][%d], unsigned& cur_key, unsigned& moved, unsigned key,
+                                          const float* base, unsigned row_bytes, int hw, int width, int height) {
+    asm volatile(
+        %s
+        : %s
+        : "r"(key), "l"(base), "r"(row_bytes), "r"(hw), "r"(width), "r"(height), "r"(width - 1), "r"(height - 1),
+          "n"(VPLUS1), "n"(TEXEL_BYTES), "n"(TEXEL_BYTES + 16));
+}
+""" % (cpt // 2, body, outs)
+    L = []
+    A = L.append
+    A("{")
+    A(".reg .pred p;")
+    A(".reg .b32 t;")
+    A(".reg .b64 u0, u1, u2, u3;")
+    A("and.b32 t, %%%d, 1 << %%%d;" % (n, n + 1))
+    A("setp.eq.u32 p, t, 0;")
+    A("@p bra DONE;")
+    rebuild_lines(A, cpt)
+    A("DONE:")
+    A("}")
+    body = "\n        ".join('"%s\\n\\t"' % x for x in L)
+    outs = ",\n          ".join(", ".join(tex_operands(cpt)[i:i + 4]) for i in range(0, 4 * cpt, 4))
+    rebuild = """// Second half: corners a, b, c, d -> A = a, B = b - a, C = c - a, D = (d - c) - (b - a) for the views issue_tok() marked.
+template <int VPLUS1>
+__device__ __forceinline__ void rebuild_tok(float2 (&t)[4][%d], unsigned moved) {
+    asm volatile(
+        %s
+        : %s
+        : "r"(moved), "n"(VPLUS1));
+}
+""" % (cpt // 2, body, outs)
+    return issue + "\n" + rebuild
+
+
 HEADER = '''// GENERATED by tools/gen_refetch.py -- do not edit by hand.
 //
 // refetch_footprint(t, key, old_key, base, W-1, H-1, row_bytes, texel_bytes)
@@ -334,5 +436,5 @@ namespace d3d {
 
 if __name__ == "__main__":
     with open(OUT, "w") as f:
-        f.write(HEADER + block(8) + "\n" + block(4) + "\n" + block_off(8) + "\n" + block_off(4) + "\n" + "\n" + block_tok(4) + "\n}  // namespace d3d\n")
+        f.write(HEADER + block(8) + "\n" + block(4) + "\n" + block_off(8) + "\n" + block_off(4) + "\n" + "\n" + block_tok(4) + "\n" + block_tok_split(4) + "\n}  // namespace d3d\n")
     print("wrote", OUT)
