@@ -171,18 +171,40 @@ __global__ void __launch_bounds__(256) regress_rawexp_kernel(const RegressParams
         acc = p.state[(size_t)p.HW + pix];
         mx = p.state[2 * (size_t)p.HW + pix];
     }
-    for (int k0 = 0; k0 < p.d_count; k0 += kGroup) {
-        float x[kGroup], d[kGroup];
+    // Resized hypotheses cost four tap loads per plane on top of the logit: all five loads of every plane of a
+    // group are issued before anything is combined (a thread then has 5 * G loads in flight; written the obvious
+    // way the compiler interleaved loads and the tap arithmetic, and the kernel sat on the long scoreboard for 11
+    // cycles per issued instruction, profiles/ncu_r1_cfg3.txt).
+    constexpr int G = (HYPS == D3D_HYPS_RESIZED) ? 4 : kGroup;
+    for (int k0 = 0; k0 < p.d_count; k0 += G) {
+        float x[G], d[G];
+        if (HYPS == D3D_HYPS_RESIZED) {
+            float t00[G], t01[G], t10[G], t11[G];
 #pragma unroll
-        for (int j = 0; j < kGroup; ++j) {
-            int k = k0 + j;
-            bool ok = k < p.d_count;
-            const float* src = p.logits ? lg + (size_t)k * p.stride_d : p.planes[ok ? k : 0] + pix;
-            x[j] = ok ? __ldg(src) : -INFINITY;
-            d[j] = ok ? hyp_at<HYPS>(p, p.d_begin + k, pix, tap) : 0.f;
+            for (int j = 0; j < G; ++j) {
+                const int k = k0 + j;
+                const bool ok = k < p.d_count;
+                const float* src = p.logits ? lg + (size_t)k * p.stride_d : p.planes[ok ? k : 0] + pix;
+                const float* q = p.hyps + (size_t)(p.d_begin + (ok ? k : 0)) * p.hh * p.hw;
+                x[j] = ok ? __ldg(src) : -INFINITY;
+                t00[j] = __ldg(q + tap.o00); t01[j] = __ldg(q + tap.o01);
+                t10[j] = __ldg(q + tap.o10); t11[j] = __ldg(q + tap.o11);
+            }
+#pragma unroll
+            for (int j = 0; j < G; ++j)                  // the expression of hyp_at<RESIZED>
+                d[j] = tap.h0 * (tap.w0 * t00[j] + tap.w1 * t01[j]) + tap.h1 * (tap.w0 * t10[j] + tap.w1 * t11[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                int k = k0 + j;
+                bool ok = k < p.d_count;
+                const float* src = p.logits ? lg + (size_t)k * p.stride_d : p.planes[ok ? k : 0] + pix;
+                x[j] = ok ? __ldg(src) : -INFINITY;
+                d[j] = ok ? hyp_at<HYPS>(p, p.d_begin + k, pix, tap) : 0.f;
+            }
         }
 #pragma unroll
-        for (int j = 0; j < kGroup; ++j) {
+        for (int j = 0; j < G; ++j) {
             if (k0 + j < p.d_count) {
                 float e = p.identity ? x[j] : expf(x[j]);   // adamvs.py:514, no max subtraction
                 mx = (mx < e) ? e : mx;            // :516-517
