@@ -339,6 +339,21 @@ __global__ void __launch_bounds__(256, (NV <= 2 && kQuadThreeCtas) ? 3 : 2) swee
                          "f"(w.z), "f"(w.w) : "memory");
         optr += p.out_sd;
     };
+    // Long sweeps (one-block re-fetch) read the staged chunk at the top of a plane and store it at the bottom, so the
+    // store never waits on shared memory (cfg2: 5.555 -> 5.462 ms); the short-sweep flavour has no registers to
+    // spare for it (stage-2 shape: 1.81 -> 1.90 ms with it) and keeps the back-to-back form.
+    constexpr bool kEarlyDrain = !kSplit;
+    float4 dw;                                       // the staged chunk this plane's iteration writes out
+    auto drain_load = [&]() {                        // top of a plane: the LDS has the whole plane to land
+        dw = lds128(dr);
+        dr += TILE_PLANE;
+    };
+    auto drain_store = [&]() {                       // bottom of the plane
+        if ((MODE != D3D_AGG_GROUP_CORR && MODE != D3D_AGG_PAIR_MEAN) || drain_row)
+            asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(optr), "f"(dw.x), "f"(dw.y),
+                         "f"(dw.z), "f"(dw.w) : "memory");
+        optr += p.out_sd;
+    };
     auto begin_drain = [&]() {
         mbar_wait(bar_d, par_d);
         bar_d += 8;
@@ -360,6 +375,7 @@ __global__ void __launch_bounds__(256, (NV <= 2 && kQuadThreeCtas) ? 3 : 2) swee
         if (draining) begin_drain();
 #pragma unroll
         for (int t = 0; t < KT; ++t) {
+            if (kEarlyDrain && draining) drain_load();
             unsigned moved = 0;
 #pragma unroll
             for (int v = 0; v < NV; ++v) moved |= __float_as_uint(g[v].w) ^ ckey[v];
@@ -460,7 +476,9 @@ __global__ void __launch_bounds__(256, (NV <= 2 && kQuadThreeCtas) ? 3 : 2) swee
                     if ((cg & (gs / 4 - 1)) == 0) sts32(tw + t * TILE_PLANE, a * gscale);
                 }
             }
-            if (draining) drain_one();
+            if (draining) {
+                if (kEarlyDrain) drain_store(); else drain_one();
+            }
         }
         // batch n is staged in ring slot slot_c: announce it (one arrival per warp)
         __syncwarp();
