@@ -340,9 +340,10 @@ __global__ void __launch_bounds__(256, (NV <= 2 && kQuadThreeCtas) ? 3 : 2) swee
         optr += p.out_sd;
     };
     // Long sweeps (one-block re-fetch) read the staged chunk at the top of a plane and store it at the bottom, so the
-    // store never waits on shared memory (cfg2: 5.555 -> 5.462 ms); the short-sweep flavour has no registers to
-    // spare for it (stage-2 shape: 1.81 -> 1.90 ms with it) and keeps the back-to-back form.
-    constexpr bool kEarlyDrain = !kSplit;
+    // store never waits on shared memory (cfg2: 5.555 -> 5.49 ms); the short-sweep flavour has no registers to
+    // spare for it (stage-2 shape: 1.81 -> 1.90 ms with it) and the group-wise volume drains a quarter of the rows
+    // (cfg4: 5.15 -> 5.26 ms with it): both keep the back-to-back form.
+    constexpr bool kEarlyDrain = !kSplit && MODE == D3D_AGG_VARIANCE;
     float4 dw;                                       // the staged chunk this plane's iteration writes out
     auto drain_load = [&]() {                        // top of a plane: the LDS has the whole plane to land
         dw = lds128(dr);
