@@ -97,3 +97,29 @@ def test_install_rebinds_the_live_reference():
             raise SystemExit("the reference's forward did not reach the engine")
     ''', extra_path=[REF])
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+def test_predict_driver_builds_the_live_reference_networks(tmp_path):
+    """`python -m deep3d_aerial_b200.predict --reference_root ...`: the reference's own network classes are
+    built with predict.py's constructor arguments, their hot path is this engine's, their checkpoints' keys are
+    untouched, and a `module.`-prefixed (nn.DataParallel) checkpoint loads."""
+    r = _run('''
+        import torch
+        from deep3d_aerial_b200 import predict, depthnets
+        for model, stage_key in (("adamvs", "DepthNet.0.reg_fuse."), ("casmvsnet", "cost_regularization.0."),
+                                 ("msrednet", "cost_regularization.0.")):
+            args = predict.build_parser().parse_args(["--data_folder", "x", "--output_folder", "y", "--model", model,
+                                                      "--numdepth", "48", "--reference_root", %r])
+            net = predict.build_model(args)
+            keys = list(net.state_dict().keys())
+            assert any(k.startswith("feature.") for k in keys) and any(k.startswith(stage_key) for k in keys), (model, keys[:5])
+            if model == "adamvs":
+                from models import adamvs
+                assert adamvs.InferDepthNet.forward is depthnets.ada_infer_forward
+                ckpt = {"model": {"module." + k: v for k, v in net.state_dict().items()}}
+                torch.save(ckpt, "ckpt.pt")
+                predict.load_checkpoint(net, "ckpt.pt")
+        print("ok")
+    ''' % REF, cwd=str(tmp_path))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
