@@ -93,6 +93,8 @@ def fuse_view(depth_ref, normal_ref, prob_ref, geometry, depth_src, normal_src, 
         t = out.get(key)
         if t is None:
             t = out[key] = torch.empty(shape, device=dev, dtype=dtype)
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError("out[%r] has shape %s, this call needs %s" % (key, tuple(t.shape), tuple(shape)))
         return _dev(t, key, dtype)
 
     a = _lib.FuseArgs()
@@ -112,6 +114,8 @@ def fuse_view(depth_ref, normal_ref, prob_ref, geometry, depth_src, normal_src, 
         a.depth_src[s] = _dev(depth_src[s], "depth_src[%d]" % s).data_ptr()
         a.normal_src[s] = _dev(normal_src[s], "normal_src[%d]" % s).data_ptr()
         if update_sources:
+            if len(out["depth_src_out"]) != s_n or tuple(out["depth_src_out"][s].shape) != (hs, ws):
+                raise ValueError("out['depth_src_out'] must hold %d maps of %dx%d" % (s_n, hs, ws))
             a.depth_src_out[s] = _dev(out["depth_src_out"][s], "depth_src_out[%d]" % s).data_ptr()
     a.mask = buf("masks", (s_n, h, w), torch.bool).data_ptr()
     a.consistent_count = buf("count", (h, w), torch.int32).data_ptr()

@@ -90,6 +90,9 @@ def test_fuse_validation_needs_no_gpu():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         fusion.fuse_view(torch.zeros(4, 4), torch.zeros(4, 4, 3), torch.zeros(4, 4), torch.zeros(2, 64, dtype=torch.float64),
                          [torch.zeros(4, 4)], [torch.zeros(4, 4, 3)])
+    with pytest.raises(ValueError, match="source views"):
+        fusion.fuse_view(torch.zeros(4, 4), torch.zeros(4, 4, 3), torch.zeros(4, 4), torch.zeros(2, 64, dtype=torch.float64),
+                         [], [])
 
 
 # ------------------------------------------------------------------------------------------------ GPU
