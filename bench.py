@@ -2,7 +2,7 @@
 """Benchmark of the plane-sweep hot path (BASELINE.json metric: cost-volume Gvoxels/s, ref views/s,
 % of HBM roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg4|cfg1] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg4|cfg1|cfg3|fuse] [--impl ours|reference]
 
 One "step" = one reference view of the workload: feature relayout (V launches), the fused
 warp+aggregate kernel (1 launch, the dominant one) and the fused softmax/regression kernel (1 launch).
@@ -14,6 +14,10 @@ max/sum joins of the timing.
 `value` is measured with inputs resident in HBM; `e2e` runs the same step from pinned HOST buffers
 (features in, depth + confidence maps out) through the public API; `--impl reference` times the
 reference's CPU PyTorch path (the oracle restatement, which calls the same ATen ops) on the host cores.
+
+The default workload, cfg2, is the configuration BASELINE.json's metric is quoted on; cfg3 (the AdaMVS 3-stage cascade
+per view) and fuse (the depth-map fusion consistency check) print the same kind of line for
+their own units of work.
 """
 from __future__ import annotations
 
