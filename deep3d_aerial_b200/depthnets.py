@@ -34,7 +34,7 @@ def _plane_loop(owner, tag, step, batch, planes, channels, hw, out_hw, state_sha
     from .graphs import PlaneLoop
 
     cache = owner.__dict__.setdefault("_d3d_plane_loops", {})
-    key = (tag, batch, planes, channels, tuple(hw), tuple(out_hw), tuple(hyps_hw), str(device))
+    key = (tag, id(step), batch, planes, channels, tuple(hw), tuple(out_hw), tuple(hyps_hw), str(device))
     if key not in cache:
         cache[key] = PlaneLoop(step, batch, planes, channels, hw, out_hw, state_shapes, device, hyps_hw=hyps_hw)
     return cache[key]
@@ -48,6 +48,21 @@ def _volume_into(out, features, proj_matrices, depth_values, mode, scenes=None, 
             w = kw.get("weights")
             sweep.cost_volume(texels, pose, depth_values[b].contiguous(), mode, plane_major=True, out=out[b], rays=rays,
                               **{**kw, "weights": None if w is None else w[b]})
+
+
+def _inference_only(what, *tensors):
+    """The kernels have no backward: a caller that expects gradients must hear about it, not train on constants.
+    (install() rebinds the classes the reference's train.py uses too.)"""
+    if not torch.is_grad_enabled():
+        return
+    for t in tensors:
+        items = t if isinstance(t, (list, tuple)) else (t,)
+        for x in items:
+            if isinstance(x, torch.Tensor) and x.requires_grad:
+                raise RuntimeError(
+                    "deep3d_aerial_b200: %s is inference only (the fused sweep kernels have no autograd backward) but was "
+                    "called with grad enabled on an input that requires grad; wrap the call in torch.no_grad(), or do "
+                    "not install() in a training process" % what)
 
 
 def _check(features, proj_matrices, depth_values, num_depth):
@@ -90,6 +105,7 @@ def cas_depthnet_forward(self, features, proj_matrices, depth_values, num_depth,
                          prob_volume_init=None):
     proj_matrices = torch.unbind(proj_matrices, 1)
     _check(features, proj_matrices, depth_values, num_depth)
+    _inference_only("cas_depthnet_forward", features, depth_values)
     volume_variance = _volume(features, proj_matrices, depth_values, sweep.AGG_VARIANCE)     # :46-60
     cost_reg = cost_regularization(volume_variance)                                             # :63
     prob_volume_pre = cost_reg.squeeze(1)
@@ -105,6 +121,7 @@ def red_depthnet_forward(self, features, proj_matrices, depth_values, num_depth,
                          prob_volume_init=None):
     proj_matrices = torch.unbind(proj_matrices, 1)
     _check(features, proj_matrices, depth_values, num_depth)
+    _inference_only("red_depthnet_forward", features, depth_values)
     volume_variance = _volume(features, proj_matrices, depth_values, sweep.AGG_VARIANCE)     # :217-230
     prob_volume_pre = cost_regularization(volume_variance).squeeze(1)
     if prob_volume_init is not None:
@@ -151,6 +168,7 @@ class _Stream:
 def red_infer_forward(self, features, proj_matrices, depth_values, num_depth, cost_regularization):
     proj_matrices = torch.unbind(proj_matrices, 1)
     _check(features, proj_matrices, depth_values, num_depth)
+    _inference_only("red_infer_forward", features, depth_values)
     ref = features[0]
     b_num, _, img_h, img_w = ref.shape
     dev = ref.device
@@ -179,6 +197,7 @@ def red_infer_forward(self, features, proj_matrices, depth_values, num_depth, co
 def ada_infer_forward(self, features, proj_matrices, depth_values, num_depth, confidence_map=None):
     proj_matrices = torch.unbind(proj_matrices, 1)
     _check(features, proj_matrices, depth_values, num_depth)
+    _inference_only("ada_infer_forward", features, depth_values, confidence_map)
     ref = features[0]
     b_num, _, img_h, img_w = ref.shape
     dev = ref.device
@@ -233,6 +252,7 @@ def ada_depthnet_forward(self, features, proj_matrices, depth_values, num_depth,
     regulariser `self.reg_fuse`, softmax + max-prob confidence."""
     proj_matrices = torch.unbind(proj_matrices, 1)
     _check(features, proj_matrices, depth_values, num_depth)
+    _inference_only("ada_depthnet_forward", features, depth_values, confidence_map)
     n_src = len(features) - 1
     _, _, img_h, img_w = features[0].shape
     pair_confidence, pair_results = [], []
@@ -248,7 +268,7 @@ def ada_depthnet_forward(self, features, proj_matrices, depth_values, num_depth,
     else:
         resized = [F.interpolate(confidence_map[i], [img_h, img_w], mode='bilinear', align_corners=False)
                    for i in range(n_src)]
-        pair_confidence.extend(resized)
+        pair_confidence = confidence_map            # adamvs.py:299: the caller's list, NOT the resized maps
         weights = torch.cat(resized, 1)
     fused = _volume(features, proj_matrices, depth_values, sweep.AGG_WEIGHTED_PRODUCT, weights=weights,
                     eps_in_numerator=True, scenes=scenes)
@@ -262,6 +282,7 @@ def ada_depthnet_forward(self, features, proj_matrices, depth_values, num_depth,
 def ucs_compute_depth(feats, proj_mats, depth_samps, cost_reg, lamb, is_training=False):
     proj_mats = torch.unbind(proj_mats, 1)
     assert len(proj_mats) == len(feats), "Different number of images and projection matrices"
+    _inference_only("ucsnet.compute_depth", feats, depth_samps)
     volume_variance = _volume(feats, proj_mats, depth_samps, sweep.AGG_VARIANCE)               # :119-134
     prob_volume_pre = cost_reg(volume_variance).squeeze(1)
     with torch.no_grad():
