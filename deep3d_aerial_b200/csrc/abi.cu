@@ -38,6 +38,7 @@ int sweep_base_pair_mean(int cpt, int nv, const SweepParams& p, dim3 grid, cudaS
 int sweep_fast_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_lean_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_quad_variance(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
+int sweep_ws_variance(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream);
 int sweep_quad_group_corr(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_quad_weighted_product(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_quad_pair_mean(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
@@ -171,7 +172,12 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
             if (int rc = make_grid(fl2, grid)) return rc;
             int rc = -1;
             // 32-channel features: the four-planes-per-pass kernel (variant 6 keeps the two-plane one for A/B)
-            if ((variant == 0 || variant == 2) && fcpt == 4 && (C == 32 || C == 16))
+            // variant 8: the warp-specialised kernel (sweep_ws.cuh: producer warps project and prefetch moved footprints
+            // into shared-memory slots with TMA, consumer warps only do the packed arithmetic).  Parity-green; 6.5 ms
+            // against sweep_quad's 5.46 ms at cfg2 so far (producer-bound), hence not the default yet.  7 = sweep_quad.
+            if (variant == 8 && fcpt == 4 && C == 32)
+                rc = sweep_ws_variance(nv, p, grid, stream);
+            if (rc < 0 && (variant == 0 || variant == 2 || variant == 7 || variant == 8) && fcpt == 4 && (C == 32 || C == 16))
                 rc = sweep_quad_variance(nv, p, grid, stream, variant == 2);
             if (rc < 0 && variant != 4 && variant != 5) rc = sweep_lean_variance(fcpt, nv, p, grid, stream, variant == 2);
             if (rc < 0) rc = sweep_fast_variance(fcpt, nv, p, grid, stream, variant == 2);

@@ -282,7 +282,9 @@ CASES = [  # v, c, d, h, w, perpixel
 
 # kernel variants (include/d3d_sweep.h): 0 = production kernel, 1 = baseline kernel, 2 = production kernel
 # with __fdiv_rn instead of the shared-reciprocal division, 3 = production kernel with 8 channels per lane
-VARIANTS = [0, 1, 2, 3, 4, 5]
+# 7 = the four-planes-per-pass kernel (sweep_quad.cuh), spelled out; 8 = the warp-specialised kernel (sweep_ws.cuh:
+# TMA-prefetched footprints, producer / consumer warps) wherever it is instantiated (32-channel features)
+VARIANTS = [0, 1, 2, 3, 4, 5, 7, 8]
 
 
 @pytest.mark.parametrize("v,c,d,h,w,perpixel", CASES)
@@ -496,7 +498,8 @@ def test_texel_relayout_round_trip():
 # ------------------------------------------------------------------ (3) properties at full size
 @pytest.mark.parametrize("mode,kw", [(sweep.AGG_VARIANCE, {"variant": 0}), (sweep.AGG_VARIANCE, {"variant": 1}),
                                      (sweep.AGG_VARIANCE, {"variant": 2}), (sweep.AGG_VARIANCE, {"variant": 3}),
-                                     (sweep.AGG_VARIANCE, {"variant": 4}),
+                                     (sweep.AGG_VARIANCE, {"variant": 4}), (sweep.AGG_VARIANCE, {"variant": 7}),
+                                     (sweep.AGG_VARIANCE, {"variant": 8}),
                                      (sweep.AGG_GROUP_CORR, {"groups": 8})])
 def test_full_size_config_against_cuda_aten_on_plane_subsets(mode, kw):
     """BASELINE.json configs 2 and 4 (V=5, C=32, D=384, 688x464): the whole volume is built in one launch;
@@ -528,6 +531,28 @@ def test_full_size_config_against_cuda_aten_on_plane_subsets(mode, kw):
     vol_p = sweep.cost_volume(tex[perm].contiguous(), sweep.relative_poses(proj[0][perm]), hyps, mode, d_begin=100,
                               d_count=8, **kw)
     assert rel_norm_err(vol_p, vol[:, 100:108]) < 1e-5
+    del vol
+    torch.cuda.empty_cache()
+
+
+def test_full_size_config_every_plane_against_cuda_aten():
+    """BASELINE.json config 2, ALL 384 planes of the launch the benchmark times (the production kernel, variant 0)
+    against the reference's ATen path on this GPU, 48 planes at a time (the ATen temporaries of a chunk fit)."""
+    rig = synth.make_rig(num_views=5)
+    h, w, c, d = 688, 464, 32, 384
+    feats = synth.make_features(5, c, h, w, seed=1).to(DEV)
+    proj = torch.from_numpy(rig.proj(4)).unsqueeze(0).to(DEV)
+    hyps = synth.uniform_hypotheses(rig.dmin, rig.dmax, d, device=DEV)
+    vol = sweep.cost_volume(sweep.to_texels(feats), sweep.relative_poses(proj[0]), hyps, sweep.AGG_VARIANCE)
+    views = [feats[i:i + 1] for i in range(5)]
+    worst = 0.0
+    for d0 in range(0, d, 48):
+        want = sweep_torch.variance_volume(views, proj, hyps[d0:d0 + 48].unsqueeze(0))[0]
+        err = float((vol[:, d0:d0 + 48] - want).abs().max() / want.abs().max())      # on the device: 2 GB per chunk
+        worst = max(worst, err)
+        del want
+        assert err < VOL_TOL, "planes %d..%d: %.3e" % (d0, d0 + 47, err)
+    print("cfg2, all %d planes against CUDA-ATen: worst chunk rel err %.3e" % (d, worst))
     del vol
     torch.cuda.empty_cache()
 

@@ -415,6 +415,96 @@ __device__ __forceinline__ void rebuild_tok(float2 (&t)[4][%d], unsigned moved) 
     return issue + "\n" + rebuild
 
 
+def block_ws(cpt, shift):
+    """Consumer side of the warp-specialised sweep (sweep_ws.cuh).  `info` is what the producer warp published for this
+    (pixel, view, plane): 0 = the footprint did not move; bit 0 set = the four corners wait in a shared-memory slot
+    (info & ~1 = its address: [corner][32 channels], copied there by the producer with cp.async, corners outside the
+    image already zero); otherwise 2 | (x0 + 8) << 2 | (y0 + 8) << 17 = the floor corner, to be fetched from global
+    memory here (the slot region was full).  Either way the corners become A, B, C, D in place; with `shift` the
+    reference texel is subtracted from A (variance is shift invariant: the reference view then contributes 0)."""
+    n = 4 * cpt
+    info, laneoff, base, rowb, wid, hei, texb, texb16 = (n + i for i in range(8))
+    ref0 = n + 8
+    L = []
+    A = L.append
+    A("{")
+    A(".reg .pred p, q, px0, px1, py0, py1;")
+    A(".reg .b32 x0, y0, x1, y1, t, sa;")
+    A(".reg .b64 w, pa, pc, u0, u1, u2, u3;")
+    A("setp.eq.u32 p, %%%d, 0;" % info)
+    A("@p bra DONE;")
+    A("and.b32 t, %%%d, 1;" % info)
+    A("setp.eq.u32 q, t, 0;")
+    A("@q bra DIRECT;")
+    A("add.u32 sa, %%%d, %%%d;" % (info, laneoff))          # laneoff = lane's channel offset in a texel - 1
+    for k in range(4):
+        for c in range(0, cpt, 4):
+            b = k * cpt + c
+            A("ld.shared.v4.f32 {%%%d, %%%d, %%%d, %%%d}, [sa+%d];" % (b, b + 1, b + 2, b + 3, 128 * k + 4 * c))
+    A("bra REBUILD;")
+    A("DIRECT:")
+    A("shr.u32 x0, %%%d, 2;" % info)
+    A("and.b32 x0, x0, 0x7fff;")
+    A("sub.s32 x0, x0, 8;")
+    A("shr.u32 y0, %%%d, 17;" % info)
+    A("sub.s32 y0, y0, 8;")
+    A("mad.lo.s32 t, y0, %%%d, x0;" % wid)
+    A("mad.wide.s32 pa, t, %%%d, %%%d;" % (texb, base))
+    A("cvt.u64.u32 w, %%%d;" % rowb)
+    A("add.s64 pc, pa, w;")
+    A("add.s32 x1, x0, 1;")
+    A("add.s32 y1, y0, 1;")
+    A("setp.lt.u32 px0, x0, %%%d;" % wid)
+    A("setp.lt.u32 px1, x1, %%%d;" % wid)
+    A("setp.lt.u32 py0, y0, %%%d;" % hei)
+    A("setp.lt.u32 py1, y1, %%%d;" % hei)
+    for i in range(n):
+        A("mov.f32 %%%d, 0f00000000;" % i)
+    for k, (ptr, off, pxn, pyn) in enumerate([("pa", 0, "px0", "py0"), ("pa", 1, "px1", "py0"), ("pc", 0, "px0", "py1"), ("pc", 1, "px1", "py1")]):
+        A("and.pred q, %s, %s;" % (pxn, pyn))
+        for c in range(0, cpt, 4):
+            b = k * cpt + c
+            if off:
+                o = "+%%%d" % (texb16 if c else texb)
+            else:
+                o = "+16" if c else ""
+            A("@q ld.global.nc.v4.f32 {%%%d, %%%d, %%%d, %%%d}, [%s%s];" % (b, b + 1, b + 2, b + 3, ptr, o))
+    A("REBUILD:")
+    for c in range(0, cpt, 2):
+        a, b, cc, d = c, cpt + c, 2 * cpt + c, 3 * cpt + c
+        for reg, i in (("u0", a), ("u1", b), ("u2", cc), ("u3", d)):
+            A("mov.b64 %s, {%%%d, %%%d};" % (reg, i, i + 1))
+        A("sub.rn.f32x2 u1, u1, u0;")
+        A("sub.rn.f32x2 u3, u3, u2;")
+        A("sub.rn.f32x2 u2, u2, u0;")
+        A("sub.rn.f32x2 u3, u3, u1;")
+        for reg, i in (("u1", b), ("u2", cc), ("u3", d)):
+            A("mov.b64 {%%%d, %%%d}, %s;" % (i, i + 1, reg))
+        if shift:
+            A("mov.b64 u1, {%%%d, %%%d};" % (ref0 + c, ref0 + c + 1))
+            A("sub.rn.f32x2 u0, u0, u1;")
+            A("mov.b64 {%%%d, %%%d}, u0;" % (a, a + 1))
+    A("DONE:")
+    A("}")
+    body = "\n        ".join('"%s\\n\\t"' % x for x in L)
+    ops = tex_operands(cpt)
+    outs = ",\n          ".join(", ".join(ops[i:i + 4]) for i in range(0, len(ops), 4))
+    refs = ", ".join('"f"(ref[%d].%s)' % (c // 2, "xy"[c % 2]) for c in range(cpt)) if shift else ""
+    name = "consume_ws_shift" if shift else "consume_ws"
+    sig_ref = ", const float2 (&ref)[%d]" % (cpt // 2) if shift else ""
+    return """// %s: see block_ws in tools/gen_refetch.py.
+template <int TEXEL_BYTES>
+__device__ __forceinline__ void %s(float2 (&t)[4][%d], unsigned info, unsigned lane_off, const float* base,
+                                   unsigned row_bytes, int width, int height%s) {
+    asm volatile(
+        %s
+        : %s
+        : "r"(info), "r"(lane_off), "l"(base), "r"(row_bytes), "r"(width), "r"(height), "n"(TEXEL_BYTES),
+          "n"(TEXEL_BYTES + 16)%s);
+}
+""" % (name, name, cpt // 2, sig_ref, body, outs, (",\n          " + refs) if shift else "")
+
+
 HEADER = '''// GENERATED by tools/gen_refetch.py -- do not edit by hand.
 //
 // refetch_footprint(t, key, old_key, base, W-1, H-1, row_bytes, texel_bytes)
@@ -436,5 +526,5 @@ namespace d3d {
 
 if __name__ == "__main__":
     with open(OUT, "w") as f:
-        f.write(HEADER + block(8) + "\n" + block(4) + "\n" + block_off(8) + "\n" + block_off(4) + "\n" + "\n" + block_tok(4) + "\n" + block_tok_split(4) + "\n}  // namespace d3d\n")
+        f.write(HEADER + block(8) + "\n" + block(4) + "\n" + block_off(8) + "\n" + block_off(4) + "\n" + "\n" + block_tok(4) + "\n" + block_tok_split(4) + "\n" + block_ws(4, True) + "\n" + block_ws(4, False) + "\n}  // namespace d3d\n")
     print("wrote", OUT)
