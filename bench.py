@@ -48,8 +48,10 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg3", "fuse"],
-                    help="cfg2 = the configuration the metric is quoted on; cfg3 = the AdaMVS 3-stage cascade")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg3", "cfg5", "fuse"],
+                    help="cfg2 = the configuration the metric is quoted on; cfg3 = the AdaMVS 3-stage cascade; "
+                         "cfg5 = a scene block of --block-views reference views dealt to the ranks (strong scaling)")
+    ap.add_argument("--block-views", type=int, default=64, help="cfg5: reference views in the scene block")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (A/B; 0 = production)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -293,6 +295,70 @@ def cpu_baseline(wl):
             "sample": "%d of %d depth planes at full %dx%d (best of 2), torch %s CPU" % (planes, d, h, w, torch.__version__)}
 
 
+def block_image_ids(i, n_block, v):
+    """Image ids of reference view i of a scene block of n_block images (the viewpair structure of the reference's
+    workspace: the V - 1 nearest neighbours along the strip, datasets/data_io.py viewpair lists): the reference image
+    first, then the other images of the window of V consecutive images that contains it."""
+    start = min(max(i - (v - 1) // 2, 0), max(n_block - v, 0))
+    return [i] + [j for j in range(start, start + v) if j != i]
+
+
+def e2e_block(args, wl, dev, rank, slots, views, n_block, warm_views=2):
+    """Runs the reference views `views` (indices into a scene block of `n_block` images) through
+    pipeline.ViewPipeline from pinned host memory, in order; returns the e2e record with the wall-clock `seconds`
+    of the timed part (the caller joins the ranks).  A few views of ANOTHER block warm the pipeline up first, so
+    nothing of the timed block is resident when the clock starts: its first view uploads all V images."""
+    import torch
+
+    from deep3d_aerial_b200 import shard, sweep
+    from deep3d_aerial_b200.pipeline import ViewPipeline
+
+    v, c, d, h, w, mode, groups, _ = WORKLOADS[wl]
+    agg = sweep.AGG_GROUP_CORR if mode == "gwc" else sweep.AGG_VARIANCE
+    pipe = ViewPipeline(v, c, h, w, d, dev, mode=agg, groups=groups, variant=args.variant, resident_images=3 * v)
+    # host side of the block: a pool of distinct pinned per-image feature maps (image j -> pool[j % len(pool)])
+    g = torch.Generator(device="cpu").manual_seed(4321 + rank)
+    pool = [torch.randn(c, h, w, generator=g, dtype=torch.float32).pin_memory() for _ in range(2 * v + 1)]
+    host = [tuple(t.cpu().pin_memory() for t in (sl[1], sl[2])) for sl in slots]
+    logit_slots = [sl[3] for sl in slots]
+    sink = 0.0
+
+    def run(view_ids, block, tag):
+        nonlocal sink
+        for k, i in enumerate(view_ids):
+            ids = block_image_ids(i, block, v)
+            hp, hh = host[k % 2]
+            lg = logit_slots[k % 2]
+            pipe.submit([pool[j % len(pool)] for j in ids], hp, hh, lambda vol, lg=lg: lg,    # regulariser: out of scope
+                        image_ids=[(tag, j) for j in ids])
+            if k:
+                dep, conf = pipe.collect()
+                sink += float(dep[0, 0]) + float(conf[0, 0])      # the host touches every result
+        if view_ids:
+            dep, conf = pipe.collect()
+            sink += float(dep[0, 0]) + float(conf[0, 0])
+
+    run(list(range(warm_views)), warm_views + v, "warm-up block")
+    views = list(views)
+    b0, n0 = pipe.h2d_bytes_total, pipe.views_submitted
+    shard.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run(views, n_block, "block")
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    done = max(1, pipe.views_submitted - n0)
+    if not math.isfinite(sink):
+        raise SystemExit("bench.py: the end-to-end pass produced non-finite maps")
+    return {"seconds": dt, "h2d_bytes_per_step": (pipe.h2d_bytes_total - b0) // done, "d2h_bytes_per_step": pipe.d2h_bytes,
+            "h2d_bytes_per_step_without_image_residency": pipe.h2d_bytes,
+            "ms_per_step": dt / done * 1e3, "steps": len(views), "timer": "host wall clock around submit/collect",
+            "stream": "a scene block walked in order (viewpair windows of %d consecutive images): a view uploads only "
+                      "the images not yet resident on its GPU (LRU of %d per-image feature maps); the first view of "
+                      "the timed block uploads all %d" % (v, 3 * v, v),
+            "image_hits": pipe.lru.hits, "image_misses": pipe.lru.misses}
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -363,42 +429,18 @@ def run_ours(args):
     achieved = b1 / (k1_ms * 1e-3) / 1e9
 
     # ---- end to end from pinned host buffers through the public API (deep3d_aerial_b200.pipeline):
-    # every step copies its features/cameras/hypotheses host->device and its depth+confidence maps
-    # device->host; neighbouring views' copies overlap the sweep (two input slots, copy + compute streams)
+    # every rank walks its own scene block in order; a reference view copies host->device the feature maps of the
+    # images that are not on the device yet (consecutive views of a block share 4 of their 5 images, see
+    # block_image_ids), its cameras and hypotheses, and device->host its depth + confidence maps; neighbouring
+    # views' copies overlap the sweep (two input slots, copy + compute streams).  The timed block starts on images
+    # the device has never seen: its first view uploads all V of them.
     e2e = None
     if not args.no_e2e:
-        from deep3d_aerial_b200.pipeline import ViewPipeline
-
         del texels, volume
         torch.cuda.empty_cache()
-        pipe = ViewPipeline(v, c, h, w, d, dev, mode=agg, groups=groups, variant=args.variant)
-        host = [tuple(t.cpu().pin_memory() for t in (s[0], s[1], s[2])) for s in slots]
-        logit_slots = [s[3] for s in slots]
-        n_e2e = max(3, args.steps)          # the first view's copy has nothing to hide behind: amortised as in a scene block
-        sink = 0.0
-
-        def run(n):
-            nonlocal sink
-            for i in range(n):
-                hf, hp, hh = host[i % 2]
-                lg = logit_slots[i % 2]
-                pipe.submit(hf, hp, hh, lambda vol, lg=lg: lg)    # the regulariser is out of scope: resident logits
-                if i:
-                    dep, conf = pipe.collect()
-                    sink += float(dep[0, 0]) + float(conf[0, 0])  # the host touches every result
-            dep, conf = pipe.collect()
-            sink += float(dep[0, 0]) + float(conf[0, 0])
-
-        run(2)
-        shard.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        run(n_e2e)
-        torch.cuda.synchronize()
-        dt = shard.join_max(time.perf_counter() - t0)
-        e2e = {"value": shard.join_sum(vox * n_e2e) / dt / 1e9, "unit": "Gvoxel/s",
-               "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
-               "ms_per_step": dt / n_e2e * 1e3, "steps": n_e2e, "timer": "host wall clock around submit/collect"}
+        n_e2e = max(3, args.steps)
+        e2e = e2e_block(args, wl, dev, rank, slots, range(n_e2e), n_e2e + v - 1)
+        e2e = dict({"value": shard.join_sum(vox * n_e2e) / shard.join_max(e2e.pop("seconds")) / 1e9, "unit": "Gvoxel/s"}, **e2e)
 
     total_launches = int(shard.join_sum(launches))
     if rank != 0:
@@ -582,6 +624,64 @@ def run_cascade(args):
     return 0
 
 
+# --------------------------------------------------------------------------- scene block across ranks (cfg5)
+def run_scene_block(args):
+    """BASELINE.json config 5: ONE scene block of --block-views reference views (cfg2 shape each) dealt to the ranks
+    with shard.partition(..., "contiguous") -- neighbouring views, which share 4 of their 5 images, stay on one GPU --
+    and run end to end from pinned host memory through pipeline.ViewPipeline (reference: the serial loop of
+    mvs/mvs_cas/predict.py:126-133 over a block of IO/params_io.py:430-444).  Strong scaling: the block is fixed,
+    every rank's pipeline starts cold (its first view uploads all V images) and the job ends with its slowest rank."""
+    import torch
+
+    from deep3d_aerial_b200 import _lib, shard
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the sweep engine has no CPU path")
+    _lib.load()
+    torch.set_grad_enabled(False)
+    rank, world, local = shard.init()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    wl = "cfg2"
+    v, c, d, h, w, mode, groups, desc = WORKLOADS[wl]
+    vox, b1, b2, brel = algorithmic_bytes(wl)
+    n_block = args.block_views
+    mine = shard.partition(list(range(n_block)), world, rank, "contiguous")
+    slots = [make_inputs(wl, 1000 * rank + s, dev) for s in range(2)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    rec = e2e_block(args, wl, dev, rank, slots, mine, n_block, warm_views=max(3, args.warmup))
+    clocks = sampler.stop()
+    launches = int(shard.join_sum(_lib.launch_count() - launches0))
+    seconds = shard.join_max(rec.pop("seconds"))
+    h2d = shard.join_sum(rec["h2d_bytes_per_step"] * len(mine)) / n_block
+    if rank != 0:
+        return 0
+    value = n_block * vox / seconds / 1e9
+    peak, peak_src = measured_peak()
+    line = {
+        "metric": "cost-volume Gvoxels/s", "value": value, "unit": "Gvoxel/s", "n_gpus": world, "steps": n_block,
+        "warmup": max(3, args.warmup), "ms_per_step": seconds / n_block * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "scene block of %d reference views, each %s; dealt contiguously to %d rank(s), end to end "
+                               "from pinned host memory" % (n_block, desc, world),
+                   "views_per_rank": len(mine), "sharding": "reference views, no collective",
+                   "l2": "every view's volume (15.69 GB) exceeds the 126 MB L2"},
+        "ref_views_per_s": n_block / seconds,
+        "roofline": {"bound": "hbm", "achieved": n_block * (b1 + b2) / seconds / 1e9 / world, "peak": peak, "unit": "GB/s",
+                     "frac": n_block * (b1 + b2) / seconds / 1e9 / world / peak, "traffic": None,
+                     "kernel": "whole view end to end (sweep + regression), per GPU", "algorithmic_bytes": b1 + b2,
+                     "peak_source": peak_src},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": dict({"value": value, "unit": "Gvoxel/s"}, **dict(rec, h2d_bytes_per_step=int(h2d))),
+        "cpu_baseline": None,
+        "note": "BASELINE.json config 5 (views/s of a fixed block); the headline line is the default --workload cfg2",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 # ------------------------------------------------------------------------------------------------ row f3
 def run_fuse(args):
     """the depth-map fusion consistency check of one reference view against its 10 source
@@ -709,11 +809,13 @@ def run_fuse(args):
 def main():
     args = parse()
     if args.impl == "reference":
-        if args.workload in ("cfg3", "fuse"):
+        if args.workload in ("cfg3", "cfg5", "fuse"):
             args.workload = "cfg2"     # the reference arm is quoted on the headline configuration
         return run_reference(args)
     if args.workload == "cfg3":
         return run_cascade(args)
+    if args.workload == "cfg5":
+        return run_scene_block(args)
     if args.workload == "fuse":
         return run_fuse(args)
     return run_ours(args)

@@ -672,6 +672,45 @@ def test_view_pipeline_matches_direct_calls():
     assert pipe.h2d_bytes == 4 * (v * c * h * w + 16 * v + d) and pipe.d2h_bytes == 8 * h * w
 
 
+@pytest.mark.parametrize("capacity", [15, 10])
+def test_view_pipeline_image_residency_uploads_each_image_once_and_builds_the_same_volumes(capacity):
+    """ViewPipeline.submit(image_ids=...): the views of a scene block share their images; feature maps of resident
+    images are not copied again, evicted buffers are not refilled under a sweep that still reads them, and every view
+    gets the volume of ITS images (the regulariser here reads the volume, so a wrong image shows in the depth)."""
+    from deep3d_aerial_b200.pipeline import ViewPipeline
+
+    v, c, d, h, w, n_img = 5, 32, 8, 40, 48, 11
+    rig, proj, _, hyps = _scene(v, c, d, h, w, seed=7)
+    g = torch.Generator().manual_seed(99)
+    images = [torch.randn(c, h, w, generator=g).pin_memory() for _ in range(n_img)]
+    pr, hy = proj[0].contiguous().pin_memory(), hyps[0].contiguous().pin_memory()
+    pipe = ViewPipeline(v, c, h, w, d, DEV, resident_images=capacity)
+    regulariser = lambda vol: (-4.0 * vol.mean(0)).contiguous()           # noqa: E731
+    windows = [[i] + [j for j in range(min(max(i - 2, 0), n_img - v), min(max(i - 2, 0), n_img - v) + v) if j != i]
+               for i in range(n_img)]
+    order = list(range(n_img)) + [0, 1]                 # ... and back to images that were evicted meanwhile
+    got = []
+    for k, i in enumerate(order):
+        pipe.submit([images[j] for j in windows[i]], pr, hy, regulariser, image_ids=windows[i])
+        if k:
+            dep, conf = pipe.collect()
+            got.append((dep.clone(), conf.clone()))
+    dep, conf = pipe.collect()
+    got.append((dep.clone(), conf.clone()))
+    for i, (dep, conf) in zip(order, got):
+        feats = torch.stack([images[j] for j in windows[i]]).to(DEV)
+        vol = sweep.cost_volume(sweep.to_texels(feats), sweep.relative_poses(pr.to(DEV)), hy.to(DEV), sweep.AGG_VARIANCE)
+        r = sweep.depth_regress(regulariser(vol), hy.to(DEV), want_index=False)
+        assert torch.equal(dep, r["depth"].cpu()) and torch.equal(conf, r["conf"].cpu()), "view %d" % i
+    assert pipe.lru.hits + pipe.lru.misses == v * len(order)
+    if capacity >= n_img:   # every image is uploaded exactly once, the return visits find theirs resident
+        assert pipe.lru.misses == n_img
+    else:                   # the return visits re-upload what the walk evicted
+        assert n_img < pipe.lru.misses <= n_img + v
+    per_image = 4 * c * h * w
+    assert pipe.h2d_bytes_total == pipe.lru.misses * per_image + len(order) * 4 * (16 * v + d)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_one_process_two_devices():
     """The shared-memory opt-in of the sweep kernels is a per-device attribute: a process that drives a second
