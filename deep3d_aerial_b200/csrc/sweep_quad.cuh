@@ -39,6 +39,9 @@ __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y
 constexpr bool kQuadThreeCtas = true;   // <= 2 source views: 32 footprint registers, three CTAs per SM
 constexpr int kQuadPlanes = 4;       // planes per pass = planes per staged batch
 constexpr int kQuadBuffers = 4;      // staging ring
+__host__ __device__ constexpr int quad_dot_rows(int mode, int gs, int c) {
+    return mode == D3D_AGG_PAIR_MEAN ? 4 : (gs == 4 ? c / 4 : c);
+}
 
 template <int NV, int TEXB, int V = 0>
 struct RefetchTok {
@@ -81,13 +84,36 @@ struct RefetchRebuild<NV, NV> {
     static __device__ __forceinline__ void run(float2 (&)[NV][4][2], unsigned) {}
 };
 
+// Correlation volumes with cached corner dot products (kDot): per view the lane keeps PA..PD = sum over its channels of
+// ref_c * {A_c, B_c, C_c, D_c} (refetch_dot, sweep_refetch.cuh) instead of the 16 coefficients themselves.
+template <int NV, int TEXB, int V = 0>
+struct RefetchDot {
+    static __device__ __forceinline__ void run(float (&dot)[NV][4], unsigned (&ckey)[NV], const float4 (&g)[NV],
+                                               const float* base, unsigned row_bytes, int hw, int W, int H,
+                                               const float (&ref)[4]) {
+        refetch_dot<V + 1, TEXB>(dot[V], ckey[V], __float_as_uint(g[V].w), base, row_bytes, hw, W, H, ref);
+        RefetchDot<NV, TEXB, V + 1>::run(dot, ckey, g, base, row_bytes, hw, W, H, ref);
+    }
+};
+template <int NV, int TEXB>
+struct RefetchDot<NV, TEXB, NV> {
+    static __device__ __forceinline__ void run(float (&)[NV][4], unsigned (&)[NV], const float4 (&)[NV], const float*, unsigned,
+                                               int, int, int, const float (&)[4]) {}
+};
+
 // MODE: D3D_AGG_VARIANCE, D3D_AGG_WEIGHTED_PRODUCT (both write C rows per plane) or D3D_AGG_GROUP_CORR
 // (p.groups rows; a lane's 4 channels are whole groups, one group, or a slice of a group that spans lanes).
 // D3D_AGG_PAIR_MEAN writes one row per source view (mean over all channels of ref * warped).
 // GS: channels per group known at compile time (4 = the G=8 configuration of BASELINE.json), 0 = read p.groups.
 // kSplit: two-phase re-fetch (short sweeps, where most planes re-fetch: cascade stages 1 and 2).
-template <int NV, int MODE, bool kIeeeDiv, bool kPerPix, int GS = 0, int LPP = 8, bool kSplit = false>
-__global__ void __launch_bounds__(256, (NV <= 2 && kQuadThreeCtas) ? 3 : 2) sweep_quad_kernel(const SweepParams p) {
+// kDot: the correlation modes (group-wise with >= 4 channels per group, pair mean) on cached corner dot products: what a
+// plane costs a lane is 3 FMAs per view, whatever the group size (cfg4: 5.15 -> see DESIGN.md), and the footprint cache is
+// 16 registers instead of 64, so three or four CTAs fit an SM.
+template <int NV, int MODE, bool kIeeeDiv, bool kPerPix, int GS = 0, int LPP = 8, bool kSplit = false, bool kDot = false>
+__global__ void __launch_bounds__(256, kDot ? 3 : (NV <= 2 && kQuadThreeCtas) ? 3 : 2)
+sweep_quad_kernel(const SweepParams p) {
+    static_assert(!kDot || ((MODE == D3D_AGG_GROUP_CORR || MODE == D3D_AGG_PAIR_MEAN) && LPP == 8 && !kSplit),
+                  "dot-product cache: correlation volumes of 32-channel features, one-block re-fetch");
     constexpr int CPT = 4, PPW = 32 / LPP, NP = 2, C = CPT * LPP;
     constexpr int PIX = 8 * PPW;                           // pixels per CTA: 32, 64 or 128
     constexpr int JPL = 8 / LPP;                           // projection chains a lane runs per pass
@@ -96,7 +122,10 @@ __global__ void __launch_bounds__(256, (NV <= 2 && kQuadThreeCtas) ? 3 : 2) swee
     constexpr int VS = NV <= 2 ? 2 : 4;                    // view slots of the table
     constexpr unsigned GEO_PLANE = VS * PPW * 16;          // bytes: one plane's table of one warp
     constexpr unsigned GEO_BUF = KT * GEO_PLANE;
-    constexpr unsigned TILE_PLANE = C * PIX * 4;           // bytes: one staged plane (4 KB whatever LPP)
+    // rows of a staged plane: the channels, or -- with the dot-product cache -- only the rows the mode writes (8 groups of
+    // cfg4, the <= 4 pair volumes), which leaves room for a fourth CTA per SM
+    constexpr int ROWS = kDot ? quad_dot_rows(MODE, GS, C) : C;
+    constexpr unsigned TILE_PLANE = ROWS * PIX * 4;        // bytes: one staged plane (4 KB for ROWS = C, whatever LPP)
     static_assert(MODE != D3D_AGG_PAIR_MEAN || LPP == 8, "pair-mean volumes are built from 32-channel features");
     constexpr unsigned TILE_BUF = KT * TILE_PLANE;
     constexpr unsigned TILE_RING = NBUF * TILE_BUF;
@@ -164,15 +193,19 @@ __global__ void __launch_bounds__(256, (NV <= 2 && kQuadThreeCtas) ? 3 : 2) swee
     const int pp0 = (LPP == 8) ? (cg >> 2) : 0;            // plane pair of chain 0 (chains k >= NVL: pair 1)
 
     float2 tex[NV][4][NP];      // per view: A, B, C, D of the current 2x2 footprint
+    float dotc[NV][4];          // kDot: their dot products with the reference texel instead
     unsigned ckey[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
         ckey[v] = 0x7fff7fffu;  // no footprint has this corner
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 4; ++k) {
+            dotc[v][k] = 0.f;
 #pragma unroll
             for (int j = 0; j < NP; ++j) tex[v][k][j] = f2(0.f, 0.f);
+        }
     }
+    const float rfs[4] = {rf[0].x, rf[0].y, rf[1].x, rf[1].y};
     const float* feats_c = p.feats + choff;
     const unsigned row_bytes = (unsigned)p.W * (unsigned)(C * 4);
 
@@ -331,12 +364,13 @@ __global__ void __launch_bounds__(256, (NV <= 2 && kQuadThreeCtas) ? 3 : 2) swee
     int slot_c = 0, slot_d = 0;
 
     auto drain_one = [&]() {
-        const float4 w = lds128(dr);
-        dr += TILE_PLANE;
         // the volume is write-once: keep it out of L1, which holds the texels the re-fetches hit
-        if ((MODE != D3D_AGG_GROUP_CORR && MODE != D3D_AGG_PAIR_MEAN) || drain_row)
+        if ((MODE != D3D_AGG_GROUP_CORR && MODE != D3D_AGG_PAIR_MEAN) || drain_row) {
+            const float4 w = lds128(dr);             // (rows past the mode's own are not even staged when ROWS < C)
             asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(optr), "f"(w.x), "f"(w.y),
                          "f"(w.z), "f"(w.w) : "memory");
+        }
+        dr += TILE_PLANE;
         optr += p.out_sd;
     };
     // Long sweeps (one-block re-fetch) read the staged chunk at the top of a plane and store it at the bottom, so the
@@ -381,7 +415,9 @@ __global__ void __launch_bounds__(256, (NV <= 2 && kQuadThreeCtas) ? 3 : 2) swee
 #pragma unroll
             for (int v = 0; v < NV; ++v) moved |= __float_as_uint(g[v].w) ^ ckey[v];
             if (moved) {                             // some footprint moved: re-fetch those (in place)
-                if constexpr (kSplit) {
+                if constexpr (kDot) {
+                    RefetchDot<NV, C * 4>::run(dotc, ckey, g, feats_c, row_bytes, p.HW, p.W, p.H, rfs);
+                } else if constexpr (kSplit) {
                     unsigned mv = 0;
                     RefetchIssue<NV, C * 4>::run(tex, ckey, mv, g, feats_c, row_bytes, p.HW, p.W, p.H);
                     RefetchRebuild<NV>::run(tex, mv);
@@ -394,8 +430,17 @@ __global__ void __launch_bounds__(256, (NV <= 2 && kQuadThreeCtas) ? 3 : 2) swee
 
             float2 s[NP], sq[NP];                    // variance: sum, sum of squares; otherwise s = accumulator
             float pm[4] = {0.f, 0.f, 0.f, 0.f};      // pair mean: this lane's partial dot product per view
+            float dsum = 0.f;                        // kDot, group-wise: sum over the views
+            if constexpr (kDot) {
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
+                for (int v = 0; v < NV; ++v) {
+                    const float o = fmaf(g[v].z, dotc[v][3], fmaf(g[v].y, dotc[v][2], fmaf(g[v].x, dotc[v][1], dotc[v][0])));
+                    pm[v] = o;
+                    dsum = v == 0 ? o : dsum + o;
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < (kDot ? 0 : NV); ++v) {
                 const float2 fx = splat(g[v].x), fy = splat(g[v].y), fxy = splat(g[v].z);
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
@@ -472,7 +517,7 @@ __global__ void __launch_bounds__(256, (NV <= 2 && kQuadThreeCtas) ? 3 : 2) swee
                     sts32(tw + t * TILE_PLANE, (0.f + s[0].x + s[0].y) * gscale);
                     sts32(tw + PIX * 4 + t * TILE_PLANE, (0.f + s[1].x + s[1].y) * gscale);
                 } else {
-                    float a = ((s[0].x + s[0].y) + s[1].x) + s[1].y;       // the lane's 4 channels, in order
+                    float a = kDot ? dsum : ((s[0].x + s[0].y) + s[1].x) + s[1].y;   // the lane's 4 channels, in order
                     for (int o = 1; o < gs / 4; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
                     if ((cg & (gs / 4 - 1)) == 0) sts32(tw + t * TILE_PLANE, a * gscale);
                 }
@@ -510,6 +555,25 @@ int launch_sweep_quad(const SweepParams& p, dim3 grid, cudaStream_t stream, bool
     // two-phase re-fetch for the short sweeps of the cascade (48 / 32 / 8 planes: a footprint lasts 1-3 planes, most
     // planes re-fetch: -13 % / -10 % on the stage-1 / stage-2 shapes); the one-block form for long sweeps (384 planes,
     // 9 % re-fetch rate: the two-phase form costs 1 % there).  A/B: variant 18 forces it, variant 32 forbids it.
+    // correlation volumes whose groups span at least a lane's 4 channels (and the pair volumes): the dot-product cache;
+    // A/B: variant 48 (flags bit 5) keeps the coefficient cache
+    if constexpr ((MODE == D3D_AGG_GROUP_CORR || MODE == D3D_AGG_PAIR_MEAN) && LPP == 8) {
+        const bool wide = MODE == D3D_AGG_PAIR_MEAN || (p.groups > 0 && p.C / p.groups >= 4);
+        if (wide && !ieee_div && !(p.flags & 32)) {
+            const size_t smem_dot = smem - (size_t)kQuadBuffers * kQuadPlanes * 32 * 4 * (32 - quad_dot_rows(MODE, g8 ? 4 : 0, 32));
+            const size_t smem_req = (p.flags & 8) ? 120 * 1024 : smem_dot;
+            void (*kd)(const SweepParams);
+            if (g8) kd = p.perpix ? sweep_quad_kernel<NV, MODE, false, true, 4, LPP, false, true>
+                                  : sweep_quad_kernel<NV, MODE, false, false, 4, LPP, false, true>;
+            else    kd = p.perpix ? sweep_quad_kernel<NV, MODE, false, true, 0, LPP, false, true>
+                                  : sweep_quad_kernel<NV, MODE, false, false, 0, LPP, false, true>;
+            static SmemOptIn opted_dot[2][2];
+            if (int rc = opted_dot[g8 ? 1 : 0][p.perpix ? 1 : 0].ensure(kd, smem_req)) return rc;
+            kd<<<grid, 256, smem_req, stream>>>(p);
+            count_launch();
+            return check_launch("sweep_quad_kernel (dot cache)");
+        }
+    }
     const bool split = !(p.flags & 16) && ((p.flags & 2) != 0 || p.d_end - p.d_begin <= 128) && !ieee_div && !g8;
     if (split) {
         kern = p.perpix ? sweep_quad_kernel<NV, MODE, false, true, 0, LPP, true>

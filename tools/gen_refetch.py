@@ -505,6 +505,81 @@ __device__ __forceinline__ void %s(float2 (&t)[4][%d], unsigned info, unsigned l
 """ % (name, name, cpt // 2, sig_ref, body, outs, (",\n          " + refs) if shift else "")
 
 
+def block_dot(cpt):
+    """Token-keyed re-fetch for the correlation volumes (group-wise correlation, AdaMVS pair volumes): what those
+    modes need of a footprint is sum_c ref_c * (A_c + fx B_c + fy C_c + fxy D_c) over the lane's channels, i.e. the
+    four DOT PRODUCTS PA = sum ref_c A_c, PB, PC, PD -- 4 registers per view instead of 16, and 3 FMAs per view and
+    plane instead of 3 per channel.  The corners live in block-local registers only while the dots are formed."""
+    n = 4                                   # outputs: PA, PB, PC, PD
+    old, key, base, rowb, hw, wid, hei, wm1, hm1, vplus1, texb, texb16 = (n + i for i in range(12))
+    ref0 = n + 12
+    L = []
+    A = L.append
+    A("{")
+    A(".reg .pred p, q, r, px0, px1, py0, py1;")
+    A(".reg .b32 x0, y0, x1, y1, t;")
+    A(".reg .b64 w, pa, pc, u0, u1, u2, u3;")
+    A(".reg .f32 ca<%d>, cb<%d>, cc<%d>, cd<%d>;" % (cpt, cpt, cpt, cpt))
+    A("setp.eq.u32 p, %%%d, %%%d;" % (key, old))
+    A("@p bra SAME;")
+    A("mov.u32 %%%d, %%%d;" % (old, key))
+    A("bfe.s32 x0, %%%d, 0, 16;" % key)
+    A("bfe.s32 y0, %%%d, 16, 16;" % key)
+    A("mad.lo.s32 t, y0, %%%d, x0;" % wid)
+    A("mad.lo.s32 t, %%%d, %%%d, t;" % (hw, vplus1))
+    A("mad.wide.s32 pa, t, %%%d, %%%d;" % (texb, base))
+    A("cvt.u64.u32 w, %%%d;" % rowb)
+    A("add.s64 pc, pa, w;")
+    A("setp.lt.u32 q, x0, %%%d;" % wm1)
+    A("setp.lt.u32 r, y0, %%%d;" % hm1)
+    A("and.pred q, q, r;")
+    A("@!q bra SPECIAL;")
+    names = ["ca", "cb", "cc", "cd"]
+    for k, (ptr, off) in enumerate([("pa", 0), ("pa", 1), ("pc", 0), ("pc", 1)]):
+        o = ("+%%%d" % texb) if off else ""
+        A("ld.global.nc.v4.f32 {%s0, %s1, %s2, %s3}, [%s%s];" % (names[k], names[k], names[k], names[k], ptr, o))
+    A("bra REBUILD;")
+    A("SPECIAL:")
+    A("add.s32 x1, x0, 1;")
+    A("add.s32 y1, y0, 1;")
+    A("setp.lt.u32 px0, x0, %%%d;" % wid)
+    A("setp.lt.u32 px1, x1, %%%d;" % wid)
+    A("setp.lt.u32 py0, y0, %%%d;" % hei)
+    A("setp.lt.u32 py1, y1, %%%d;" % hei)
+    for nm in names:
+        for c in range(cpt):
+            A("mov.f32 %s%d, 0f00000000;" % (nm, c))
+    for k, (ptr, off, pxn, pyn) in enumerate([("pa", 0, "px0", "py0"), ("pa", 1, "px1", "py0"), ("pc", 0, "px0", "py1"), ("pc", 1, "px1", "py1")]):
+        A("and.pred q, %s, %s;" % (pxn, pyn))
+        o = ("+%%%d" % texb) if off else ""
+        A("@q ld.global.nc.v4.f32 {%s0, %s1, %s2, %s3}, [%s%s];" % (names[k], names[k], names[k], names[k], ptr, o))
+    A("REBUILD:")
+    for c in range(cpt):
+        A("sub.rn.f32 cb%d, cb%d, ca%d;" % (c, c, c))       # B = b - a
+        A("sub.rn.f32 cd%d, cd%d, cc%d;" % (c, c, c))       # d - c
+        A("sub.rn.f32 cc%d, cc%d, ca%d;" % (c, c, c))       # C = c - a
+        A("sub.rn.f32 cd%d, cd%d, cb%d;" % (c, c, c))       # D = (d - c) - (b - a)
+    for out, nm in enumerate(names):
+        A("mul.rn.f32 %%%d, %%%d, %s0;" % (out, ref0, nm))
+        for c in range(1, cpt):
+            A("fma.rn.f32 %%%d, %%%d, %s%d, %%%d;" % (out, ref0 + c, nm, c, out))
+    A("SAME:")
+    A("}")
+    body = "\n        ".join('"%s\\n\\t"' % x for x in L)
+    return """// Dot-product variant (sweep_quad.cuh, correlation volumes): see block_dot in tools/gen_refetch.py.  `dot` = {PA, PB, PC,
+// PD} of this lane's %d channels against the reference texel `ref`; `cur_key` is updated in place.
+template <int VPLUS1, int TEXEL_BYTES>
+__device__ __forceinline__ void refetch_dot(float (&dot)[4], unsigned& cur_key, unsigned key, const float* base,
+                                            unsigned row_bytes, int hw, int width, int height, const float (&ref)[%d]) {
+    asm volatile(
+        %s
+        : "+f"(dot[0]), "+f"(dot[1]), "+f"(dot[2]), "+f"(dot[3]), "+r"(cur_key)
+        : "r"(key), "l"(base), "r"(row_bytes), "r"(hw), "r"(width), "r"(height), "r"(width - 1), "r"(height - 1),
+          "n"(VPLUS1), "n"(TEXEL_BYTES), "n"(TEXEL_BYTES + 16), %s);
+}
+""" % (cpt, cpt, body, ", ".join('"f"(ref[%d])' % c for c in range(cpt)))
+
+
 HEADER = '''// GENERATED by tools/gen_refetch.py -- do not edit by hand.
 //
 // refetch_footprint(t, key, old_key, base, W-1, H-1, row_bytes, texel_bytes)
@@ -526,5 +601,5 @@ namespace d3d {
 
 if __name__ == "__main__":
     with open(OUT, "w") as f:
-        f.write(HEADER + block(8) + "\n" + block(4) + "\n" + block_off(8) + "\n" + block_off(4) + "\n" + "\n" + block_tok(4) + "\n" + block_tok_split(4) + "\n" + block_ws(4, True) + "\n" + block_ws(4, False) + "\n}  // namespace d3d\n")
+        f.write(HEADER + block(8) + "\n" + block(4) + "\n" + block_off(8) + "\n" + block_off(4) + "\n" + "\n" + block_tok(4) + "\n" + block_tok_split(4) + "\n" + block_ws(4, True) + "\n" + block_ws(4, False) + "\n" + block_dot(4) + "\n}  // namespace d3d\n")
     print("wrote", OUT)
