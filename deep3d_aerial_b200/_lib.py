@@ -17,7 +17,7 @@ AGG_WARP, AGG_VARIANCE, AGG_GROUP_CORR, AGG_WEIGHTED_PRODUCT, AGG_PAIR_MEAN = 0,
 SOFTMAX_STABLE, SOFTMAX_RAW_EXP, SOFTMAX_NONE = 0, 1, 2
 CONF_MAX_PROB, CONF_WINDOW4 = 0, 1
 HYPS_UNIFORM, HYPS_PER_PIXEL, HYPS_RESIZED = 0, 1, 2
-SAMPLES_RANGE, SAMPLES_AROUND, SAMPLES_CASCADE = 0, 1, 2
+SAMPLES_RANGE, SAMPLES_AROUND, SAMPLES_CASCADE, SAMPLES_SPREAD = 0, 1, 2, 3
 
 _f32p = C.c_void_p  # device pointers travel as integers
 
@@ -55,7 +55,7 @@ class SamplesArgs(C.Structure):
         ("full_height", C.c_int32), ("full_width", C.c_int32),
         ("dmin", C.c_float), ("dmax", C.c_float), ("reserved0", C.c_int32),
         ("interval", C.c_double),
-        ("cur", _f32p), ("out", _f32p),
+        ("cur", _f32p), ("out", _f32p), ("spread", _f32p),
     ]
 
 
@@ -85,6 +85,8 @@ EXPORTS = {
     "d3d_depth_samples": (C.c_int, [C.POINTER(SamplesArgs), C.c_void_p]),
     "d3d_consistency_fuse": (C.c_int, [C.POINTER(FuseArgs), C.c_void_p]),
     "d3d_pixel_rays": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "d3d_homo_warp_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_void_p, C.c_void_p]),
     "d3d_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "d3d_last_error": (C.c_char_p, []),
     "d3d_version": (C.c_int, []),

@@ -132,20 +132,27 @@ __global__ void __launch_bounds__(kFuseThreads) consistency_fuse_kernel(const Fu
         div_pair(kx, ky, kz, fxs, fys);
         fxs += 0.5;
         fys += 0.5;
-        long long at;
+        // `at`: where the source maps are read; `at_used`: the source pixel a consistent reference pixel consumes,
+        // (x_src[mask] + 0.5).astype(int) ON THE INTEGER x_src (:123-124) = x_src, or x_src + 1 where it is negative
+        // (truncation towards zero), wrapped by the same index rule.  They differ only for wrapped (negative) coordinates.
+        long long at, at_used;
         double xsd, ysd;
         if (fabs(fxs) < 2147483000.0 && fabs(fys) < 2147483000.0) {      // (NaN fails the test)
             int xi = __double2int_rz(fxs), yi = __double2int_rz(fys);
             xsd = (double)xi;
             ysd = (double)yi;
-            if ((unsigned)xi >= (unsigned)p.Ws) { xi %= p.Ws; if (xi < 0) xi += p.Ws; }    // CuPy's wrap-around
-            if ((unsigned)yi >= (unsigned)p.Hs) { yi %= p.Hs; if (yi < 0) yi += p.Hs; }
-            at = (long long)yi * p.Ws + xi;
+            if ((unsigned)xi < (unsigned)p.Ws && (unsigned)yi < (unsigned)p.Hs) {
+                at = at_used = (long long)yi * p.Ws + xi;
+            } else {                                                     // CuPy's wrap-around
+                at = wrap((long long)yi, p.Hs) * p.Ws + wrap((long long)xi, p.Ws);
+                at_used = wrap((long long)yi + (yi < 0), p.Hs) * p.Ws + wrap((long long)xi + (xi < 0), p.Ws);
+            }
         } else {                                                         // astype(int) is int64 upstream
             const long long xs = __double2ll_rz(fxs), ys = __double2ll_rz(fys);
             xsd = (double)xs;
             ysd = (double)ys;
             at = wrap(ys, p.Hs) * p.Ws + wrap(xs, p.Ws);
+            at_used = wrap(ys + (ys < 0), p.Hs) * p.Ws + wrap(xs + (xs < 0), p.Ws);
         }
         const float sd = __ldg(p.depth_src[s] + at);
         const float* np_ = p.normal_src[s] + 3 * at;
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(kFuseThreads) consistency_fuse_kernel(const Fu
             ay = __fadd_rn(ay, __fmul_rn(conf, fy));
             az = __fadd_rn(az, __fmul_rn(conf, fz));
             aconf += conf;
-            if (p.depth_src_out[s]) p.depth_src_out[s][at] = 0.f;   // consumed by this reference view (:128-131)
+            if (p.depth_src_out[s]) p.depth_src_out[s][at_used] = 0.f;   // consumed by this reference view (:123-126)
         }
         const long long o = (long long)s * hw + pix;
         if (p.mask) p.mask[o] = ok;

@@ -12,6 +12,7 @@ namespace d3d {
 
 struct SamplesParams {
     const float* __restrict__ cur;
+    const float* __restrict__ spread;
     float* __restrict__ out;
     int mode, D, H, W, HW;
     int sh, sw, fh, fw;
@@ -57,6 +58,14 @@ __global__ void __launch_bounds__(256) depth_samples_kernel(const SamplesParams 
         float step = __fdiv_rn(__fsub_rn(hi, lo), dm1);
         for (int k = 0; k < p.D; ++k)
             p.out[(size_t)k * p.HW + pix] = __fadd_rn(lo, __fmul_rn((float)k, step));
+        return;
+    }
+    if (p.mode == D3D_SAMPLES_SPREAD) {          // ucsnet.py:41-51: low + step * i + eps, every step rounded as torch rounds it
+        const float c = __ldg(p.cur + pix), e = __ldg(p.spread + pix);
+        const float lo = __fsub_rn(c, e), hi = __fadd_rn(c, e);
+        const float step = __fdiv_rn(__fsub_rn(hi, lo), dm1);
+        for (int k = 0; k < p.D; ++k)
+            p.out[(size_t)k * p.HW + pix] = __fadd_rn(__fadd_rn(lo, __fmul_rn(step, (float)k)), 1e-12f);
         return;
     }
     // CASCADE: four full-resolution taps of the tri-linear down-sampling (the depth axis keeps its
@@ -141,7 +150,7 @@ extern "C" int d3d_depth_samples(const D3dSamplesArgs* a, void* cuda_stream) {
     if (a->struct_size != sizeof(D3dSamplesArgs))
         return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_samples: struct_size %u != %zu", a->struct_size,
                     sizeof(D3dSamplesArgs));
-    if (a->mode < D3D_SAMPLES_RANGE || a->mode > D3D_SAMPLES_CASCADE)
+    if (a->mode < D3D_SAMPLES_RANGE || a->mode > D3D_SAMPLES_SPREAD)
         return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_samples: unknown mode %d", a->mode);
     if (a->num_depth < 2 || a->height <= 0 || a->width <= 0)
         return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_samples: need D >= 2 and positive extent (D=%d H=%d W=%d)",
@@ -151,11 +160,13 @@ extern "C" int d3d_depth_samples(const D3dSamplesArgs* a, void* cuda_stream) {
     if (!a->out) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_samples: out is NULL");
     if (a->mode == D3D_SAMPLES_AROUND && !a->cur)
         return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_samples: AROUND needs cur");
+    if (a->mode == D3D_SAMPLES_SPREAD && (!a->cur || !a->spread))
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_samples: SPREAD needs cur and spread");
     if (a->mode == D3D_SAMPLES_CASCADE && a->cur &&
         (a->src_height <= 0 || a->src_width <= 0 || a->full_height <= 0 || a->full_width <= 0))
         return fail(D3D_ERR_BAD_ARGUMENT, "d3d_depth_samples: CASCADE needs src and full extents");
     SamplesParams p;
-    p.cur = a->cur; p.out = a->out; p.mode = a->mode; p.D = a->num_depth;
+    p.cur = a->cur; p.spread = a->spread; p.out = a->out; p.mode = a->mode; p.D = a->num_depth;
     p.H = a->height; p.W = a->width; p.HW = a->height * a->width;
     p.sh = a->src_height; p.sw = a->src_width; p.fh = a->full_height; p.fw = a->full_width;
     p.half_span = (float)((double)a->num_depth / 2.0 * a->interval);
@@ -179,6 +190,69 @@ __global__ void __launch_bounds__(256) pixel_rays_kernel(const float* __restrict
     o[0] = fmaf(m[2], 1.f, fmaf(m[1], (float)py, m[0] * (float)px));
     o[HW] = fmaf(m[6], 1.f, fmaf(m[5], (float)py, m[4] * (float)px));
     o[2 * (size_t)HW] = fmaf(m[10], 1.f, fmaf(m[9], (float)py, m[8] * (float)px));
+}
+
+// homo_warping_double (module.py:560-601): one thread per (pixel, plane); coordinates in fp64 exactly as the reference
+// forms them (cuBLAS dgemm accumulates the 3-term product with FMAs: fma(r2, 1, fma(r1, y, r0*x))), the normalised
+// grid cast to fp32, then ATen's fp32 unnormalisation and bilinear weights (GridSampler.cu: nw = (ix_se-ix)*(iy_se-iy)...).
+__global__ void __launch_bounds__(256) warp_f64_kernel(const float* __restrict__ tex, const double* __restrict__ pose,
+                                                       const float* __restrict__ hyps, int perpix, int C, int D, int H, int W,
+                                                       float* __restrict__ out) {
+    const int HW = H * W;
+    const int pix = blockIdx.x * 256 + threadIdx.x;
+    const int d = blockIdx.y;
+    if (pix >= HW) return;
+    const int py = pix / W, px = pix - py * W;
+    const double x = (double)px, y = (double)py;
+    const double depth = (double)__ldg(hyps + (perpix ? (size_t)d * HW + pix : (size_t)d));
+    double q[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double ray = fma(pose[4 * r + 2], 1.0, fma(pose[4 * r + 1], y, __dmul_rn(pose[4 * r], x)));
+        q[r] = __dadd_rn(__dmul_rn(ray, depth), pose[4 * r + 3]);
+    }
+    const double hw2 = (double)(W - 1) / 2.0, hh2 = (double)(H - 1) / 2.0;       // python floats: (width - 1) / 2
+    const float gx = (float)__dsub_rn(__ddiv_rn(__ddiv_rn(q[0], q[2]), hw2), 1.0);
+    const float gy = (float)__dsub_rn(__ddiv_rn(__ddiv_rn(q[1], q[2]), hh2), 1.0);
+    float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)(W - 1));  // GridSampler.h:27-32, align_corners
+    float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(H - 1));
+    ix = fminf(fmaxf(ix, -2.f), (float)(W - 1) + 2.f);                           // NaN / far outside: every corner out
+    iy = fminf(fmaxf(iy, -2.f), (float)(H - 1) + 2.f);
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    const float ax = __fsub_rn(__fadd_rn(fx0, 1.f), ix), bx = __fsub_rn(ix, fx0);
+    const float ay = __fsub_rn(__fadd_rn(fy0, 1.f), iy), by = __fsub_rn(iy, fy0);
+    const float w[4] = {__fmul_rn(ax, ay), __fmul_rn(bx, ay), __fmul_rn(ax, by), __fmul_rn(bx, by)};
+    const float* t[4];
+    bool in[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
+        in[k] = (unsigned)xx < (unsigned)W && (unsigned)yy < (unsigned)H;
+        t[k] = tex + ((size_t)(in[k] ? yy : 0) * W + (in[k] ? xx : 0)) * C;
+    }
+    float* o = out + (size_t)d * HW + pix;
+    for (int c = 0; c < C; ++c) {
+        float acc = 0.f;                                                       // ATen accumulates nw, ne, sw, se in order
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (in[k]) acc = __fadd_rn(acc, __fmul_rn(__ldg(t[k] + c), w[k]));
+        o[(size_t)c * D * HW] = acc;
+    }
+}
+
+extern "C" int d3d_homo_warp_f64(const float* texels, const double* pose64, const float* hyps, int32_t hyps_per_pixel,
+                                 int32_t channels, int32_t num_depth, int32_t height, int32_t width, float* out,
+                                 void* cuda_stream) {
+    if (!texels || !pose64 || !hyps || !out) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_homo_warp_f64: texels/pose64/hyps/out is NULL");
+    if (channels <= 0 || num_depth <= 0 || height < 2 || width < 2 || num_depth > 65535)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_homo_warp_f64: bad extent C=%d D=%d H=%d W=%d", channels, num_depth, height, width);
+    if ((long long)height * width > INT32_MAX / 2) return fail(D3D_ERR_UNSUPPORTED, "d3d_homo_warp_f64: H*W too large");
+    const int hw = height * width;
+    warp_f64_kernel<<<dim3((hw + 255) / 256, num_depth), 256, 0, (cudaStream_t)cuda_stream>>>(
+        texels, pose64, hyps, hyps_per_pixel != 0, channels, num_depth, height, width, out);
+    count_launch();
+    return check_launch("warp_f64_kernel");
 }
 
 extern "C" int d3d_pixel_rays(const float* pose, int32_t num_src, int32_t height, int32_t width, float* out, void* cuda_stream) {

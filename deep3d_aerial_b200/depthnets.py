@@ -291,16 +291,16 @@ def ucs_compute_depth(feats, proj_mats, depth_samps, cost_reg, lamb, is_training
 
 
 def ucs_uncertainty_samples(cur_depth, exp_var, ndepth, device, dtype, shape):
-    """ucsnet.py:30-53.  The first-stage branch is get_depth_range_samples' range branch; the
-    per-pixel branch is a handful of element-wise ops on [B,1,H,W] maps and stays in PyTorch."""
+    """ucsnet.py:30-53.  The first-stage branch is get_depth_range_samples' range branch; the per-pixel branch
+    (cur -/+ exp_var in ndepth steps, + 1e-12) is d3d_depth_samples' SPREAD mode: one launch writes the [D,H,W] planes."""
     if cur_depth.dim() == 2:
         from .module import get_depth_range_samples
         return get_depth_range_samples(cur_depth, ndepth, 0.0, device, dtype, shape)
-    low_bound = cur_depth - exp_var
-    high_bound = cur_depth + exp_var
     assert ndepth > 1
-    step = (high_bound - low_bound) / (float(ndepth) - 1)
-    return torch.cat([low_bound + step * i + 1e-12 for i in range(int(ndepth))], 1)
+    with torch.no_grad():
+        return torch.stack([sweep.depth_samples(sweep.SAMPLES_SPREAD, int(ndepth), cur_depth.shape[-2:],
+                                                cur=cur_depth[b, 0].contiguous(), spread=exp_var[b, 0].contiguous())
+                            for b in range(cur_depth.shape[0])], 0)
 
 
 # ------------------------------------------------------------------ nn.Module wrappers (parameter-free)

@@ -240,7 +240,12 @@ def fuse_block(view_list, depths, normals, confidences, intrinsics, extrinsics, 
                 depths[s] = new                              # tmp/<src>_init.pfm
             masks.append(out["masks"])
             first = False
-        if first:                                            # empty source list
+        if first:
+            # no usable source: upstream still fuses the view (fusion_3d_normal.py:436-541 with an empty loop) -- every
+            # pixel counts itself only, so with min_consistent > 1 nothing survives and tmp/<ref>_init.pfm is all zeros:
+            # views fused later see an emptied map, not the original one
+            if min_consistent > 1:
+                depths[ref] = torch.zeros_like(depths[ref])
             continue
         depths[ref] = out["depth_ref_filtered"]              # tmp/<ref>_init.pfm
         res = {"count": out["count"], "xyz": out["xyz"], "final_mask": out["final_mask"],
@@ -286,6 +291,11 @@ class FusionPipeline:
                                "(its slot would be overwritten)" % len(self.slots))
         self._next = (self._next + 1) % len(self.slots)
         up, compute, down = self.streams
+        # the caller's device tensors (source maps, or reference maps handed over on the device) were produced on ITS
+        # stream: neither the upload nor the kernel may run ahead of that
+        producer = torch.cuda.current_stream(self.dev)
+        up.wait_stream(producer)
+        compute.wait_stream(producer)
         if isinstance(geometry, np.ndarray):
             s["copied"].synchronize()                         # the slot's previous upload has left its pinned block
             s["geom_host"].copy_(torch.from_numpy(geometry))
@@ -300,8 +310,10 @@ class FusionPipeline:
         with torch.cuda.stream(compute):
             compute.wait_event(s["copied"])
             compute.wait_event(s["downloaded"])               # the slot's previous results have left
+            # (the pipeline treats the source maps as read-only: the per-source "consumed pixels" copies of fuse_view
+            # would be S device-to-device copies per view that nobody reads here -- fuse_block is the stateful loop)
             s["out"] = fuse_view(s["depth"], s["normal"], s["prob"], s["geom"], depth_src, normal_src, out=s["out"],
-                                 **self.th)
+                                 update_sources=False, **self.th)
             s["done"].record()
         with torch.cuda.stream(down):
             down.wait_event(s["done"])

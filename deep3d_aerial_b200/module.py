@@ -44,9 +44,33 @@ def homo_warping_float(src_fea, src_proj, ref_proj, depth_values):
 
 
 def homo_warping_double(src_fea, src_proj, ref_proj, depth_values):
-    """module.py:560-601 does the coordinate arithmetic in fp64 and casts the grid back to fp32; no model
-    calls it.  Served by the fp32 kernel (same sampling, coordinates differ by fp32 rounding only)."""
-    return homo_warping_float(src_fea, src_proj, ref_proj, depth_values)
+    """module.py:560-601: the warp with the coordinate arithmetic in fp64.  src_fea [B,C,H,W] fp32, src_proj / ref_proj
+    [B,4,4] **fp64** (upstream multiplies `rot` by an fp64 pixel grid and torch.matmul does not promote, so fp32
+    projections fail there with a dtype error; here too), depth_values [B,D] or [B,D,H,W] -> [B,C,D,H,W] fp32.
+    No model calls it; d3d_homo_warp_f64 keeps the contract: fp64 up to the normalised grid, fp32 sampling."""
+    import ctypes as C
+
+    from . import _lib
+
+    if src_proj.dtype != torch.float64 or ref_proj.dtype != torch.float64:
+        raise RuntimeError("expected m1 and m2 to have the same dtype, but got: %s != double (homo_warping_double needs "
+                           "fp64 projection matrices, as the reference does)" % str(src_proj.dtype).replace("torch.", ""))
+    if not src_fea.is_cuda:
+        raise RuntimeError("src_fea is on %s: the sweep engine only runs on CUDA (no CPU fallback)" % src_fea.device)
+    batch, channels, height, width = src_fea.shape
+    num_depth = depth_values.shape[1]
+    out = torch.empty((batch, channels, num_depth, height, width), device=src_fea.device, dtype=torch.float32)
+    with torch.no_grad():
+        proj = torch.matmul(src_proj, torch.inverse(ref_proj)).contiguous()       # module.py:573, in fp64
+        lib = _lib.load()
+        stream = C.c_void_p(torch.cuda.current_stream(src_fea.device).cuda_stream)
+        for b in range(batch):
+            texels = sweep.to_texels([src_fea[b].float()])[0]
+            hyps = _hyps_item(depth_values, b).float().contiguous()
+            with torch.cuda.device(src_fea.device):
+                _lib.check(lib.d3d_homo_warp_f64(texels.data_ptr(), proj[b].data_ptr(), hyps.data_ptr(), int(hyps.dim() == 3),
+                                                 channels, num_depth, height, width, out[b].data_ptr(), stream))
+    return out
 
 
 def depth_regression(p, depth_values):

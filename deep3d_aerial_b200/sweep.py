@@ -18,7 +18,7 @@ import torch
 from . import _lib
 from ._lib import (AGG_GROUP_CORR, AGG_PAIR_MEAN, AGG_VARIANCE, AGG_WARP, AGG_WEIGHTED_PRODUCT,  # noqa: F401
                    CONF_MAX_PROB, CONF_WINDOW4, HYPS_PER_PIXEL, HYPS_RESIZED, HYPS_UNIFORM,
-                   SAMPLES_AROUND, SAMPLES_CASCADE, SAMPLES_RANGE, SOFTMAX_NONE, SOFTMAX_RAW_EXP,
+                   SAMPLES_AROUND, SAMPLES_CASCADE, SAMPLES_RANGE, SAMPLES_SPREAD, SOFTMAX_NONE, SOFTMAX_RAW_EXP,
                    SOFTMAX_STABLE)
 
 
@@ -107,8 +107,17 @@ def kernel_rays(pose: torch.Tensor, h: int, w: int) -> torch.Tensor:
     return out
 
 
-# (H, W, device) -> does cuBLAS round the reference's rot @ [x,y,1] in the kernels' own order at this size?
+# (H, W, device, matmul settings, library versions) -> does cuBLAS round the reference's rot @ [x,y,1] in the kernels'
+# own order at this size?
 _RAY_ORDER = {}
+
+
+def _ray_key(h: int, w: int, device) -> tuple:
+    """What the verdict of `rays_for` depends on besides the image size: the device, and everything that can make
+    torch.matmul pick another cuBLAS kernel or another arithmetic for an fp32 product -- TF32 permission, the
+    float32 matmul precision, the CUDA / torch build.  A change of any of them re-runs the probe."""
+    return (h, w, torch.device(device).index, bool(torch.backends.cuda.matmul.allow_tf32),
+            torch.get_float32_matmul_precision(), torch.version.cuda, torch.__version__)
 _PROBE = ((0.9931, -0.0713, 13.71, 0.0), (0.0527, 1.0117, -22.37, 0.0), (1.3e-5, -2.1e-5, 1.0031, 0.0), (0.0, 0.0, 0.0, 1.0))
 
 
@@ -123,7 +132,7 @@ def rays_for(pose: torch.Tensor, h: int, w: int) -> Optional[torch.Tensor]:
     a 10.7 ms AdaMVS view.  `D3D_RAYS=matmul` in the environment forces the matmul everywhere."""
     if os.environ.get("D3D_RAYS", "") == "matmul":           # escape hatch: always the reference's own product
         return reference_rays(pose, h, w)
-    key = (h, w, pose.device.index)
+    key = _ray_key(h, w, pose.device)
     same = _RAY_ORDER.get(key)
     if same is None:
         probe = torch.tensor(_PROBE, dtype=torch.float32, device=pose.device).unsqueeze(0)
@@ -289,7 +298,7 @@ def depth_regress(logits: torch.Tensor, hyps: torch.Tensor, *, conf_mode: int = 
 
 def depth_samples(mode: int, num_depth: int, hw: Tuple[int, int], *, device=None, cur: Optional[torch.Tensor] = None,
                   interval: float = 0.0, dmin: float = 0.0, dmax: float = 0.0,
-                  full_hw: Optional[Sequence[int]] = None) -> torch.Tensor:
+                  full_hw: Optional[Sequence[int]] = None, spread: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Depth hypotheses [D,H,W] for a stage (include/d3d_sweep.h: D3D_SAMPLES_*)."""
     h, w = int(hw[0]), int(hw[1])
     if cur is not None:
@@ -307,14 +316,20 @@ def depth_samples(mode: int, num_depth: int, hw: Tuple[int, int], *, device=None
         if cur.dim() != 2:
             raise ValueError("cur must be [h,w]")
         a.src_height, a.src_width = cur.shape
-        if mode == SAMPLES_AROUND and tuple(cur.shape) != (h, w):
-            raise ValueError("cur must be [%d,%d] for SAMPLES_AROUND" % (h, w))
+        if mode in (SAMPLES_AROUND, SAMPLES_SPREAD) and tuple(cur.shape) != (h, w):
+            raise ValueError("cur must be [%d,%d] for SAMPLES_AROUND / SAMPLES_SPREAD" % (h, w))
+    if mode == SAMPLES_SPREAD:
+        if cur is None or spread is None:
+            raise ValueError("SAMPLES_SPREAD needs cur and spread")
+        spread = _need(spread, "spread")
+        if tuple(spread.shape) != (h, w):
+            raise ValueError("spread must be [%d,%d]" % (h, w))
     if full_hw is not None:
         a.full_height, a.full_width = int(full_hw[0]), int(full_hw[1])
     else:
         a.full_height, a.full_width = h, w
     a.interval, a.dmin, a.dmax = float(interval), float(dmin), float(dmax)
-    a.cur, a.out = _ptr(cur), out.data_ptr()
+    a.cur, a.out, a.spread = _ptr(cur), out.data_ptr(), _ptr(spread if mode == SAMPLES_SPREAD else None)
     with torch.cuda.device(out.device):
         _lib.check(_lib.load().d3d_depth_samples(C.byref(a), _stream()))
     return out

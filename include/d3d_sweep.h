@@ -149,7 +149,9 @@ enum { D3D_SAMPLES_RANGE = 0,     /* [dmin,dmax] -> linspace planes broadcast to
        D3D_SAMPLES_AROUND = 1,    /* cur[H,W] -> cur -/+ D/2*interval, D planes (module.py:616-630) */
        D3D_SAMPLES_CASCADE = 2    /* Cas-MVSNet / RED-Net stage glue (cas_mvsnet.py:206-226,
                                      msrednet.py:495-515): cur[src_h,src_w] (or the range) bilinear
-                                     -> full res, samples at full res, trilinear -> [D,H,W]        */ };
+                                     -> full res, samples at full res, trilinear -> [D,H,W]        */,
+       D3D_SAMPLES_SPREAD = 3     /* UCS-Net: cur[H,W] -/+ spread[H,W] (the exp_variance map of the stage before) in D
+                                     steps, + 1e-12 (uncertainty_aware_samples, ucsnet.py:41-51)       */ };
 
 typedef struct D3dSamplesArgs {
     uint32_t struct_size;
@@ -163,6 +165,7 @@ typedef struct D3dSamplesArgs {
     double interval;           /* depth_inteval_pixel = ratio * (dmax-dmin)/num_depth_total        */
     const float* cur;          /* previous depth estimate; NULL with CASCADE = first stage (range) */
     float* out;                /* [D,H,W]                                                          */
+    const float* spread;       /* SPREAD: per-pixel half width of the sampled interval, [H,W]      */
 } D3dSamplesArgs;
 
 /* Per-stage depth-hypothesis resampling, get_depth_range_samples (module.py:633-650). */
@@ -173,6 +176,15 @@ int d3d_depth_samples(const D3dSamplesArgs* args, void* cuda_stream);
  * torch.matmul (module.py:538) once per image size to learn whether cuBLAS rounds in that order at that size; where
  * it does, the sweeps form their rays themselves and the matmul (a 0.75 TB/s skinny GEMM) is skipped. */
 int d3d_pixel_rays(const float* pose, int32_t num_src, int32_t height, int32_t width, float* out, void* cuda_stream);
+
+/* ---- homo_warping_double: the warp with fp64 coordinate arithmetic (mvs/mvs_cas/models/module.py:560-601) -----
+ * The reference forms rot @ [x,y,1], X = rot_xyz * d + trans, X/Z and u / ((W-1)/2) - 1 in fp64 (its projection
+ * matrices must be fp64 for that: torch.matmul does not promote), casts the normalised grid to fp32 and samples it with
+ * the fp32 grid_sample (bilinear, zeros padding, align_corners=True).  out[C,D,H,W] = the warped source view.
+ *   texels: [H,W,C] channels-last source features;  pose64: [4,4] row-major fp64 P_src @ inverse(P_ref);
+ *   hyps: fp32 [D] or [D,H,W] (widened to fp64 in the kernel, as `.double()` does). */
+int d3d_homo_warp_f64(const float* texels, const double* pose64, const float* hyps, int32_t hyps_per_pixel,
+                      int32_t channels, int32_t num_depth, int32_t height, int32_t width, float* out, void* cuda_stream);
 
 /* Feature relayout [C,H,W] -> [H,W,C] (the sweep kernel gathers whole texels). */
 int d3d_nchw_to_nhwc(const float* in, float* out, int32_t channels, int32_t height, int32_t width,

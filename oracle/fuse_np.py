@@ -78,7 +78,12 @@ def check(depth_ref, normal_ref, intrinsics_ref, extrinsics_ref, depth_src, norm
 
     angle = np.repeat(np.expand_dims(cos, axis=0), 3, axis=0)
     depth_rep[~mask] = 0
-    depth_src[np.mod(y_src[mask], hs), np.mod(x_src[mask], ws)] = 0
+    # consistency_check_n.py:123-126: the consumed source pixel is (x_src[mask] + 0.5).astype(int) -- on the INTEGER x_src,
+    # i.e. x_src itself where it is >= 0 and x_src + 1 where it is negative (truncation towards zero; negative
+    # coordinates only occur through the wrap-around above), then CuPy's index rule again
+    x_inv = (x_src[mask] + 0.5).astype(np.int64)
+    y_inv = (y_src[mask] + 0.5).astype(np.int64)
+    depth_src[np.mod(y_inv, hs), np.mod(x_inv, ws)] = 0
     xyz_world = src_world[0:3].reshape([3, height, width]).astype(np.float32)
     xyz_world[:, ~mask] = 0
     angle[:, ~mask] = 0
@@ -148,6 +153,11 @@ def fuse_block(view_list, depths, normals, confidences, intrinsics, extrinsics, 
             masks.append(mask)
             used.append(src)
         if not used:
+            # upstream runs the rest of the body with an empty source loop (:525-543): geo_mask_sum is 1 everywhere, so with
+            # min_consistent > 1 the final mask is empty and the view's tmp map is written as all zeros; no points are
+            # saved for it (:549-551)
+            if min_consistent > 1:
+                depths[ref] = np.zeros_like(d_ref)
             continue
         final = np.array(count >= min_consistent)
         filtered = np.array(d_ref)

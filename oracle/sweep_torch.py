@@ -73,6 +73,28 @@ def warp_source(src_fea, src_proj, ref_proj, depth_values):
     return out.view(batch, channels, num_depth, height, width)
 
 
+def warp_source_double(src_fea, src_proj, ref_proj, depth_values):
+    """`module.py:560-601` (homo_warping_double): the same warp with the coordinate arithmetic in fp64 -- fp64
+    projection matrices (upstream multiplies `rot` by an fp64 pixel grid; torch.matmul does not promote), fp32 depths
+    widened by `.double()`, the normalised grid cast back to fp32 for the fp32 `grid_sample`."""
+    batch, channels, height, width = src_fea.shape
+    num_depth = depth_values.shape[1]
+    rot, trans = relative_pose(src_proj, ref_proj)                   # fp64
+    dev = src_fea.device
+    ys, xs = torch.meshgrid(torch.arange(0, height, dtype=torch.float32, device=dev),
+                            torch.arange(0, width, dtype=torch.float32, device=dev), indexing="ij")
+    pix = torch.stack((xs.reshape(-1), ys.reshape(-1), torch.ones(height * width, device=dev)))
+    pix = pix.unsqueeze(0).repeat(batch, 1, 1).double()
+    ray = torch.matmul(rot, pix)
+    pts = ray.unsqueeze(2).repeat(1, 1, num_depth, 1) * depth_values.view(batch, 1, num_depth, -1).double()
+    pts = pts + trans.view(batch, 3, 1, 1)
+    uv = pts[:, :2] / pts[:, 2:3]
+    grid = torch.stack((uv[:, 0] / ((width - 1) / 2) - 1, uv[:, 1] / ((height - 1) / 2) - 1), dim=3).float()
+    warped = F.grid_sample(src_fea, grid.view(batch, num_depth * height, width, 2), mode="bilinear",
+                           padding_mode="zeros", align_corners=True)
+    return warped.view(batch, channels, num_depth, height, width)
+
+
 # --------------------------------------------------------------------------- a3
 def variance_volume(features, proj_matrices, depth_values):
     """`cas_mvsnet.py:46-60` (same lines in `msrednet.py:217-230`, `ucsnet.py:119-134`).

@@ -28,6 +28,17 @@ def test_warp_matches_golden(name):
         assert rel_norm_err(arb, g["warped"][0, i - 1]) < 2e-4
 
 
+@pytest.mark.parametrize("name", ["warp_double_uniform", "warp_double_perpixel"])
+def test_warp_double_matches_golden(name):
+    """homo_warping_double (module.py:560-601, fp64 coordinates) restated: bit for bit against the live reference's output."""
+    g = load_golden(name)
+    for i in range(1, g["feats"].shape[0]):
+        got = sweep_torch.warp_source_double(g["feats"][i:i + 1], g["proj"][:, i], g["proj"][:, 0], g["hyps"])
+        assert torch.equal(got, g["warped"][:, i - 1])
+    with pytest.raises(RuntimeError):       # fp32 projections: torch.matmul does not promote (upstream fails the same way)
+        sweep_torch.warp_source_double(g["feats"][1:2], g["proj"][:, 1].float(), g["proj"][:, 0].float(), g["hyps"])
+
+
 @pytest.mark.parametrize("name", ["cas_depthnet_uniform", "cas_depthnet_perpixel"])
 def test_variance_and_window4_match_golden(name):
     g = load_golden(name)

@@ -66,6 +66,21 @@ def test_homo_warping_matches_golden(name):
         assert rel_norm_err(got, g["warped"][:, i - 1]) < VOL_TOL
 
 
+@pytest.mark.parametrize("name", ["warp_double_uniform", "warp_double_perpixel"])
+def test_homo_warping_double_matches_golden(name):
+    """module.homo_warping_double -> d3d_homo_warp_f64 (fp64 coordinates, fp32 sampling) against the live reference's
+    module.py:560-601; fp32 projection matrices are refused as upstream refuses them (dtype error of torch.matmul)."""
+    g = load_golden(name)
+    for i in range(1, g["feats"].shape[0]):
+        got = module.homo_warping_double(g["feats"][i:i + 1].to(DEV), g["proj"][:, i].to(DEV), g["proj"][:, 0].to(DEV),
+                                         g["hyps"].to(DEV))
+        assert got.shape == g["warped"][:, i - 1].shape and got.dtype == torch.float32
+        assert rel_norm_err(got, g["warped"][:, i - 1]) < 1e-6
+    with pytest.raises(RuntimeError):
+        module.homo_warping_double(g["feats"][1:2].to(DEV), g["proj"][:, 1].float().to(DEV), g["proj"][:, 0].float().to(DEV),
+                                   g["hyps"].to(DEV))
+
+
 @pytest.mark.parametrize("name", ["cas_depthnet_uniform", "cas_depthnet_perpixel"])
 def test_cas_depthnet_matches_golden(name):
     g = load_golden(name)
@@ -478,6 +493,22 @@ def test_stream_batch_cadence_does_not_change_the_plane_at_a_time_models(batch_p
     assert all(torch.equal(a, b) for a, b in zip(base, got))
 
 
+def test_ucs_uncertainty_samples_are_bit_identical_to_the_reference_s_elementwise_ops():
+    """ucsnet.uncertainty_aware_samples (ucsnet.py:41-51) -> d3d_depth_samples SPREAD: cur -/+ exp_var in D steps + 1e-12,
+    every fp32 rounding in torch's order."""
+    rig = synth.tiny_rig()
+    h, w = 37, 53
+    cur = synth.smooth_depth_map(rig, h, w, seed=2).view(1, 1, h, w)
+    spread = (0.05 + torch.rand(1, 1, h, w, generator=torch.Generator().manual_seed(5))) * 0.7
+    for nd in (2, 8, 33):
+        want = sweep_torch.uncertainty_samples(cur, spread, nd)
+        got = depthnets.ucs_uncertainty_samples(cur.to(DEV), spread.to(DEV), nd, DEV, torch.float32, [1, h, w])
+        assert got.shape == want.shape and torch.equal(got.cpu(), want)
+    first = depthnets.ucs_uncertainty_samples(torch.tensor([[rig.dmin, rig.dmax]], device=DEV), None, 8, DEV, torch.float32,
+                                              [1, h, w])
+    assert torch.equal(first.cpu(), sweep_torch.depth_range_samples(torch.tensor([[rig.dmin, rig.dmax]]), 8, 0.0, [1, h, w]))
+
+
 def test_exp_variance_matches_oracle():
     d, h, w = 8, 24, 24
     logits = synth.planted_logits(d, h, w, seed=6) * 0.3
@@ -633,7 +664,7 @@ def test_rays_for_skips_the_matmul_only_where_the_kernel_order_is_the_reference_
     got = sweep.rays_for(pose_a, h, w)
     if got is not None:
         assert torch.equal(got, sweep.reference_rays(pose_a, h, w))
-        assert sweep._RAY_ORDER[(h, w, pose_a.device.index)] is False
+        assert sweep._RAY_ORDER[sweep._ray_key(h, w, pose_a.device)] is False
         return
     g = torch.Generator().manual_seed(h * 7 + w)
     for scale in (1.0, 2.0):
@@ -642,6 +673,27 @@ def test_rays_for_skips_the_matmul_only_where_the_kernel_order_is_the_reference_
         fresh[:, :2, :] /= scale
         assert torch.equal(sweep.kernel_rays(fresh, h, w), sweep.reference_rays(fresh, h, w))
     assert sweep.rays_for(fresh, h, w) is None
+
+
+def test_rays_verdict_is_retaken_when_the_matmul_settings_change():
+    """The verdict is keyed on TF32 permission / float32 matmul precision too: with TF32 allowed the reference's own
+    product is a different number, so the sweeps must be handed THAT product again, not the cached "same order"."""
+    rig = synth.make_rig(num_views=5)
+    pose = sweep.relative_poses(torch.from_numpy(rig.proj(4)).to(DEV))
+    h, w = 96, 128
+    base = sweep.rays_for(pose, h, w)
+    before = torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = not before
+        assert sweep._ray_key(h, w, pose.device) not in sweep._RAY_ORDER
+        other = sweep.rays_for(pose, h, w)
+        assert sweep._ray_key(h, w, pose.device) in sweep._RAY_ORDER
+        want = sweep.reference_rays(pose, h, w)
+        assert (other is None and torch.equal(want, sweep.kernel_rays(pose, h, w))) or torch.equal(other, want)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = before
+    again = sweep.rays_for(pose, h, w)
+    assert (again is None) == (base is None)
 
 
 def test_view_pipeline_matches_direct_calls():
