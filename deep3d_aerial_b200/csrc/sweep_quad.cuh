@@ -50,11 +50,20 @@ struct RefetchTok {
         refetch_tok<V + 1, TEXB>(tex[V], ckey[V], __float_as_uint(g[V].w), base, row_bytes, hw, W, H);
         RefetchTok<NV, TEXB, V + 1>::run(tex, ckey, g, base, row_bytes, hw, W, H);
     }
+    // variance volume of the long sweeps: A = a - ref (the reference view then contributes nothing to sum / sum of squares)
+    static __device__ __forceinline__ void run_shift(float2 (&tex)[NV][4][2], unsigned (&ckey)[NV], const float4 (&g)[NV],
+                                                     const float* base, unsigned row_bytes, int hw, int W, int H,
+                                                     const float2 (&ref)[2]) {
+        refetch_tok_shift<V + 1, TEXB>(tex[V], ckey[V], __float_as_uint(g[V].w), base, row_bytes, hw, W, H, ref);
+        RefetchTok<NV, TEXB, V + 1>::run_shift(tex, ckey, g, base, row_bytes, hw, W, H, ref);
+    }
 };
 template <int NV, int TEXB>
 struct RefetchTok<NV, TEXB, NV> {
     static __device__ __forceinline__ void run(float2 (&)[NV][4][2], unsigned (&)[NV], const float4 (&)[NV], const float*,
                                                unsigned, int, int, int) {}
+    static __device__ __forceinline__ void run_shift(float2 (&)[NV][4][2], unsigned (&)[NV], const float4 (&)[NV], const float*,
+                                                     unsigned, int, int, int, const float2 (&)[2]) {}
 };
 
 // The same in two phases (issue_tok / rebuild_tok): every moved view's loads are started before any view is rebuilt,
@@ -115,6 +124,10 @@ sweep_quad_kernel(const SweepParams p) {
     static_assert(!kDot || ((MODE == D3D_AGG_GROUP_CORR || MODE == D3D_AGG_PAIR_MEAN) && LPP == 8 && !kSplit),
                   "dot-product cache: correlation volumes of 32-channel features, one-block re-fetch");
     constexpr int CPT = 4, PPW = 32 / LPP, NP = 2, C = CPT * LPP;
+    // long variance sweeps of 32-channel features: footprints are kept relative to the reference texel (A = a - ref at
+    // re-fetch time; variance is shift invariant), so the reference view costs nothing per plane: one packed add per
+    // channel pair and plane less, 4 registers less (ref^2), and less cancellation than the reference's own form
+    constexpr bool kShift = MODE == D3D_AGG_VARIANCE && !kSplit && LPP == 8 && !kIeeeDiv;
     constexpr int PIX = 8 * PPW;                           // pixels per CTA: 32, 64 or 128
     constexpr int JPL = 8 / LPP;                           // projection chains a lane runs per pass
     constexpr int NVL = JPL > 1 ? JPL / 2 : 1;             // distinct views among them
@@ -421,6 +434,8 @@ sweep_quad_kernel(const SweepParams p) {
                     unsigned mv = 0;
                     RefetchIssue<NV, C * 4>::run(tex, ckey, mv, g, feats_c, row_bytes, p.HW, p.W, p.H);
                     RefetchRebuild<NV>::run(tex, mv);
+                } else if constexpr (kShift) {
+                    RefetchTok<NV, C * 4>::run_shift(tex, ckey, g, feats_c, row_bytes, p.HW, p.W, p.H, rf);
                 } else {
                     RefetchTok<NV, C * 4>::run(tex, ckey, g, feats_c, row_bytes, p.HW, p.W, p.H);
                 }
@@ -448,7 +463,10 @@ sweep_quad_kernel(const SweepParams p) {
                     o = __ffma2_rn(fy, tex[v][2][j], o);
                     o = __ffma2_rn(fxy, tex[v][3][j], o);
                     if (MODE == D3D_AGG_VARIANCE) {
-                        if (v == 0) {
+                        if (v == 0 && kShift) {
+                            s[j] = o;
+                            sq[j] = __fmul2_rn(o, o);
+                        } else if (v == 0) {
                             s[j] = __fadd2_rn(rf[j], o);
                             sq[j] = __ffma2_rn(o, o, rf2[j]);
                         } else {

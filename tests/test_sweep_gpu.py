@@ -299,7 +299,9 @@ CASES = [  # v, c, d, h, w, perpixel
 # with __fdiv_rn instead of the shared-reciprocal division, 3 = production kernel with 8 channels per lane
 # 7 = the four-planes-per-pass kernel (sweep_quad.cuh), spelled out; 8 = the warp-specialised kernel (sweep_ws.cuh:
 # TMA-prefetched footprints, producer / consumer warps) wherever it is instantiated (32-channel features)
-VARIANTS = [0, 1, 2, 3, 4, 5, 7, 8]
+# 32 = sweep_quad's one-block re-fetch whatever the sweep length: the form long sweeps (D > 128) run, whose variance
+# volume keeps its footprints relative to the reference texel
+VARIANTS = [0, 1, 2, 3, 4, 5, 7, 8, 32]
 
 
 @pytest.mark.parametrize("v,c,d,h,w,perpixel", CASES)
@@ -556,7 +558,12 @@ def test_full_size_config_against_cuda_aten_on_plane_subsets(mode, kw):
         print("full-size planes %d..%d %s: rel err %.3e" % (d0, d0 + 3, kw, err))
         assert err < VOL_TOL
         part = sweep.cost_volume(tex, pose, hyps, mode, d_begin=d0, d_count=4, **kw)
-        assert torch.equal(part, vol[:, d0:d0 + 4])
+        if mode == sweep.AGG_VARIANCE and kw.get("variant") in (0, 7):
+            # the 4-plane slice runs sweep_quad's short-sweep form, the 384-plane launch the long-sweep form whose
+            # footprints are kept relative to the reference texel: the same volume, rounded differently
+            assert rel_norm_err(part, vol[:, d0:d0 + 4]) < 1e-5
+        else:
+            assert torch.equal(part, vol[:, d0:d0 + 4])
     # source views are interchangeable for the aggregate (up to summation order)
     perm = [0, 3, 1, 4, 2]
     vol_p = sweep.cost_volume(tex[perm].contiguous(), sweep.relative_poses(proj[0][perm]), hyps, mode, d_begin=100,

@@ -109,8 +109,9 @@ def tex_operands(cpt):
     return ops
 
 
-def rebuild_lines(A, cpt):
-    # A = a, B = b - a, C = c - a, D = (d - c) - (b - a), packed over channel pairs
+def rebuild_lines(A, cpt, ref0=None):
+    # A = a, B = b - a, C = c - a, D = (d - c) - (b - a), packed over channel pairs; with ref0 (operand index of the
+    # lane's reference texel) A = a - ref: the variance volume is shift invariant, so the reference view drops out
     for c in range(0, cpt, 2):
         a, b, cc, d = c, cpt + c, 2 * cpt + c, 3 * cpt + c
         for reg, i in (("u0", a), ("u1", b), ("u2", cc), ("u3", d)):
@@ -121,6 +122,10 @@ def rebuild_lines(A, cpt):
         A("sub.rn.f32x2 u3, u3, u1;")
         for reg, i in (("u1", b), ("u2", cc), ("u3", d)):
             A("mov.b64 {%%%d, %%%d}, %s;" % (i, i + 1, reg))
+        if ref0 is not None:
+            A("mov.b64 u1, {%%%d, %%%d};" % (ref0 + c, ref0 + c + 1))
+            A("sub.rn.f32x2 u0, u0, u1;")
+            A("mov.b64 {%%%d, %%%d}, u0;" % (a, a + 1))
 
 
 def block_off(cpt, split=False):
@@ -235,11 +240,13 @@ __device__ __forceinline__ void refetch_off(float2 (&t)[4][%d], unsigned& cur_ke
 """ % (cpt // 2, body, outs)
 
 
-def block_tok(cpt):
+def block_tok(cpt, shift=False):
     """Token-keyed re-fetch (sweep_quad.cuh): the projecting lane publishes only the packed floor corner
-    (low 16 bits of the two round-down-add results); address and border handling live here, on the rare path."""
+    (low 16 bits of the two round-down-add results); address and border handling live here, on the rare path.
+    shift: A = a - ref (the variance volume of the long sweeps, see rebuild_lines)."""
     n = 4 * cpt
     old, key, base, rowb, hw, wid, hei, wm1, hm1, vplus1, texb, texb16 = (n + i for i in range(12))
+    ref0 = n + 12
     L = []
     A = L.append
     A("{")
@@ -290,13 +297,26 @@ def block_tok(cpt):
                 o = "+16" if c else ""
             A("@q ld.global.nc.v4.f32 {%%%d, %%%d, %%%d, %%%d}, [%s%s];" % (b, b + 1, b + 2, b + 3, ptr, o))
     A("REBUILD:")
-    rebuild_lines(A, cpt)
+    rebuild_lines(A, cpt, ref0 if shift else None)
     A("SAME:")
     A("}")
     body = "\n        ".join('"%s\\n\\t"' % x for x in L)
     ops = tex_operands(cpt)
     ops.append('"+r"(cur_key)')
     outs = ",\n          ".join(", ".join(ops[i:i + 4]) for i in range(0, len(ops), 4))
+    if shift:
+        refs = ", ".join('"f"(ref[%d].%s)' % (c // 2, "xy"[c % 2]) for c in range(cpt))
+        return """// Token-keyed re-fetch with the reference texel subtracted from A (variance volume, long sweeps): see block_tok.
+template <int VPLUS1, int TEXEL_BYTES>
+__device__ __forceinline__ void refetch_tok_shift(float2 (&t)[4][%d], unsigned& cur_key, unsigned key, const float* base,
+                                                  unsigned row_bytes, int hw, int width, int height, const float2 (&ref)[%d]) {
+    asm volatile(
+        %s
+        : %s
+        : "r"(key), "l"(base), "r"(row_bytes), "r"(hw), "r"(width), "r"(height), "r"(width - 1), "r"(height - 1),
+          "n"(VPLUS1), "n"(TEXEL_BYTES), "n"(TEXEL_BYTES + 16), %s);
+}
+""" % (cpt // 2, cpt // 2, body, outs, refs)
     return """// Token-keyed variant (sweep_quad.cuh): `key` = (y0 & 0xffff) << 16 | (x0 & 0xffff), the floor corner of the
 // footprint as it falls out of the round-down adds of the projection.  Everything else -- the texel address
 // (64-bit: no size limit on `feats`), the interior test, zeros padding at the border (loads predicated off) and
@@ -601,5 +621,5 @@ namespace d3d {
 
 if __name__ == "__main__":
     with open(OUT, "w") as f:
-        f.write(HEADER + block(8) + "\n" + block(4) + "\n" + block_off(8) + "\n" + block_off(4) + "\n" + "\n" + block_tok(4) + "\n" + block_tok_split(4) + "\n" + block_ws(4, True) + "\n" + block_ws(4, False) + "\n" + block_dot(4) + "\n}  // namespace d3d\n")
+        f.write(HEADER + block(8) + "\n" + block(4) + "\n" + block_off(8) + "\n" + block_off(4) + "\n" + "\n" + block_tok(4) + "\n" + block_tok(4, True) + "\n" + block_tok_split(4) + "\n" + block_ws(4, True) + "\n" + block_ws(4, False) + "\n" + block_dot(4) + "\n}  // namespace d3d\n")
     print("wrote", OUT)
