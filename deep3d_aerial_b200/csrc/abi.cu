@@ -39,6 +39,7 @@ int sweep_fast_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaSt
 int sweep_lean_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_quad_variance(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_ws_variance(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream);
+int sweep_pre_variance(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream);
 int sweep_quad_group_corr(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_quad_weighted_product(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_quad_pair_mean(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
@@ -177,7 +178,10 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
             // against sweep_quad's 5.46 ms at cfg2 so far (producer-bound), hence not the default yet.  7 = sweep_quad.
             if (variant == 8 && fcpt == 4 && C == 32)
                 rc = sweep_ws_variance(nv, p, grid, stream);
-            if (rc < 0 && (variant == 0 || variant == 2 || variant == 7 || variant == 8) && fcpt == 4 && (C == 32 || C == 16))
+            // variant 9: sweep_quad's formulation with the moved footprints prefetched by TMA a pass ahead (sweep_pre.cuh)
+            if (variant == 9 && fcpt == 4 && C == 32)
+                rc = sweep_pre_variance(nv, p, grid, stream);
+            if (rc < 0 && (variant == 0 || variant == 2 || variant == 7 || variant == 8 || variant == 9) && fcpt == 4 && (C == 32 || C == 16))
                 rc = sweep_quad_variance(nv, p, grid, stream, variant == 2);
             if (rc < 0 && variant != 4 && variant != 5) rc = sweep_lean_variance(fcpt, nv, p, grid, stream, variant == 2);
             if (rc < 0) rc = sweep_fast_variance(fcpt, nv, p, grid, stream, variant == 2);

@@ -80,10 +80,21 @@ __device__ __forceinline__ void emit_next(const RegressParams& p, int pix, float
 }
 
 // ---- F.softmax flavour -------------------------------------------------------------------------
-template <int HYPS>
+// PARTS threads share a pixel, each walking a contiguous quarter of the planes with its own online-softmax state; the
+// states are merged through shared memory (max of the maxima, every sum rescaled by exp(m_i - M); on a tie the part
+// with the lower planes wins, which keeps "the first plane reaching the maximum").  Why: one thread per pixel is one
+// long-running thread per pixel -- 319 232 pixels are barely more threads than the GPU holds at once (303 104), so the
+// grid ran as one full wave plus a 5 % straggler wave that cost as much as the first (0.185 ms for 490 MB = 40 % of the
+// HBM peak, profiles/ncu_r1n.txt).  Four times as many threads, each a quarter as long: ~6 waves.
+template <int HYPS, int PARTS>
 __global__ void __launch_bounds__(256) regress_softmax_kernel(const RegressParams p) {
-    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= p.HW) return;
+    constexpr int PIXB = 256 / PARTS;                  // pixels per CTA; consecutive lanes = consecutive pixels
+    __shared__ float part_state[PARTS > 1 ? PARTS : 1][6][PIXB];
+    const int pl = threadIdx.x % PIXB, part = threadIdx.x / PIXB;
+    const long long pix_raw = (long long)blockIdx.x * PIXB + pl;
+    const bool live = pix_raw < p.HW;
+    if (PARTS == 1 && !live) return;
+    const int pix = live ? (int)pix_raw : p.HW - 1;
     ResizeTap tap = {};
     if (HYPS == D3D_HYPS_RESIZED) tap = make_tap(pix / p.W, pix % p.W, p);
     const float* lg = p.logits + pix;
@@ -97,15 +108,20 @@ __global__ void __launch_bounds__(256) regress_softmax_kernel(const RegressParam
     const float dref = hyp_at<HYPS>(p, 0, pix, tap);   // shift keeps the sums well conditioned
     const bool want_var = p.expvar != nullptr;
 
-    for (int k0 = 0; k0 < p.D; k0 += kGroup) {
-        float x[kGroup], d[kGroup];
+    const int per = PARTS == 1 ? p.D : ((p.D + PARTS * kGroup - 1) / (PARTS * kGroup)) * kGroup;   // planes per part
+    const int kbeg = part * per, kend = min(p.D, kbeg + per);
+    // two groups of planes in flight: the loads of group g + 1 are issued before group g is folded in (a thread then has
+    // 16 logit loads outstanding instead of 8: the kernel is a pure stream and its speed is bytes in flight per SM)
+    auto load_group = [&](int k0, float (&x)[kGroup], float (&d)[kGroup]) {
 #pragma unroll
         for (int j = 0; j < kGroup; ++j) {
-            int k = k0 + j;
-            bool ok = k < p.D;
+            const int k = k0 + j;
+            const bool ok = k < kend;
             x[j] = ok ? __ldg(lg + (size_t)k * p.stride_d) : -INFINITY;
             d[j] = ok ? hyp_at<HYPS>(p, k, pix, tap) : dref;
         }
+    };
+    auto fold_group = [&](int k0, const float (&x)[kGroup], const float (&d)[kGroup]) {
         float gm = x[0];
 #pragma unroll
         for (int j = 1; j < kGroup; ++j) gm = fmaxf(gm, x[j]);
@@ -125,6 +141,38 @@ __global__ void __launch_bounds__(256) regress_softmax_kernel(const RegressParam
             sd = fmaf(e, dc, sd);
             sk = fmaf(e, (float)(k0 + j), sk);
             if (want_var) sdd = fmaf(e * dc, dc, sdd);
+        }
+    };
+    float xa[kGroup], da[kGroup], xb[kGroup], db[kGroup];
+    if (kbeg < kend) load_group(kbeg, xa, da);
+    for (int k0 = kbeg; k0 < kend; k0 += 2 * kGroup) {
+        if (k0 + kGroup < kend) load_group(k0 + kGroup, xb, db);
+        fold_group(k0, xa, da);
+        if (k0 + kGroup < kend) {
+            if (k0 + 2 * kGroup < kend) load_group(k0 + 2 * kGroup, xa, da);
+            fold_group(k0 + kGroup, xb, db);
+        }
+    }
+    if (PARTS > 1) {
+        part_state[part][0][pl] = m; part_state[part][1][pl] = s; part_state[part][2][pl] = sd;
+        part_state[part][3][pl] = sk; part_state[part][4][pl] = sdd; part_state[part][5][pl] = __int_as_float(arg);
+        __syncthreads();
+        if (part != 0 || !live) return;
+#pragma unroll
+        for (int i = 1; i < PARTS; ++i) {
+            const float mi = part_state[i][0][pl];
+            if (mi == -INFINITY) continue;             // a part without planes (D smaller than its start)
+            if (mi > m) {
+                const float r = expf(m - mi);
+                s *= r; sd *= r; sk *= r; sdd *= r;
+                m = mi;
+                arg = __float_as_int(part_state[i][5][pl]);
+            }
+            const float r = expf(mi - m);
+            s = fmaf(part_state[i][1][pl], r, s);
+            sd = fmaf(part_state[i][2][pl], r, sd);
+            sk = fmaf(part_state[i][3][pl], r, sk);
+            sdd = fmaf(part_state[i][4][pl], r, sdd);
         }
     }
     const float inv = 1.f / s;
@@ -230,9 +278,11 @@ __global__ void __launch_bounds__(256) regress_rawexp_kernel(const RegressParams
 template <int HYPS>
 static int launch_regress(const RegressParams& p, int softmax_mode, cudaStream_t stream) {
     dim3 grid((p.HW + 255) / 256);
-    if (softmax_mode == D3D_SOFTMAX_STABLE)
-        regress_softmax_kernel<HYPS><<<grid, 256, 0, stream>>>(p);
-    else
+    if (softmax_mode == D3D_SOFTMAX_STABLE) {
+        // long sweeps: four threads per pixel (a quarter of the planes each); short ones: one thread per pixel
+        if (p.D >= 32) regress_softmax_kernel<HYPS, 4><<<dim3((p.HW + 63) / 64), 256, 0, stream>>>(p);
+        else regress_softmax_kernel<HYPS, 1><<<grid, 256, 0, stream>>>(p);
+    } else
         regress_rawexp_kernel<HYPS><<<grid, 256, 0, stream>>>(p);
     count_launch();
     return check_launch("regress_kernel");

@@ -68,6 +68,16 @@ __device__ __forceinline__ void stg128_na(float* ptr, const float4& w) {
                  "f"(w.w) : "memory");
 }
 
+// The same footprint as two plain bulk copies (rows y0 and y0 + 1, two adjacent texels = 256 contiguous bytes each): no
+// tensor-map lookup, no coordinate arithmetic in the copy engine -- for footprints wholly inside the image only.
+__device__ __forceinline__ void bulk_footprint(unsigned dst, const float* nw_texel, unsigned row_bytes, unsigned bar) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], 512;" ::"r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 256, [%2];"
+                 ::"r"(dst), "l"(nw_texel), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 256, [%2];"
+                 ::"r"(dst + 256), "l"(reinterpret_cast<const char*>(nw_texel) + row_bytes), "r"(bar) : "memory");
+}
+
 // MODE: D3D_AGG_VARIANCE (others: sweep_quad.cuh).  kPerPix: per-pixel hypotheses [D,H,W].
 template <int NV, int MODE, bool kPerPix>
 __global__ void __launch_bounds__(384, 2) sweep_ws_kernel(const SweepParams p, const __grid_constant__ CUtensorMap texmap) {

@@ -299,9 +299,10 @@ CASES = [  # v, c, d, h, w, perpixel
 # with __fdiv_rn instead of the shared-reciprocal division, 3 = production kernel with 8 channels per lane
 # 7 = the four-planes-per-pass kernel (sweep_quad.cuh), spelled out; 8 = the warp-specialised kernel (sweep_ws.cuh:
 # TMA-prefetched footprints, producer / consumer warps) wherever it is instantiated (32-channel features)
+# 9 = sweep_quad's formulation with TMA-prefetched footprints (sweep_pre.cuh);
 # 32 = sweep_quad's one-block re-fetch whatever the sweep length: the form long sweeps (D > 128) run, whose variance
 # volume keeps its footprints relative to the reference texel
-VARIANTS = [0, 1, 2, 3, 4, 5, 7, 8, 32]
+VARIANTS = [0, 1, 2, 3, 4, 5, 7, 8, 9, 32]
 
 
 @pytest.mark.parametrize("v,c,d,h,w,perpixel", CASES)
@@ -532,7 +533,7 @@ def test_texel_relayout_round_trip():
 @pytest.mark.parametrize("mode,kw", [(sweep.AGG_VARIANCE, {"variant": 0}), (sweep.AGG_VARIANCE, {"variant": 1}),
                                      (sweep.AGG_VARIANCE, {"variant": 2}), (sweep.AGG_VARIANCE, {"variant": 3}),
                                      (sweep.AGG_VARIANCE, {"variant": 4}), (sweep.AGG_VARIANCE, {"variant": 7}),
-                                     (sweep.AGG_VARIANCE, {"variant": 8}),
+                                     (sweep.AGG_VARIANCE, {"variant": 8}), (sweep.AGG_VARIANCE, {"variant": 9}),
                                      (sweep.AGG_GROUP_CORR, {"groups": 8})])
 def test_full_size_config_against_cuda_aten_on_plane_subsets(mode, kw):
     """BASELINE.json configs 2 and 4 (V=5, C=32, D=384, 688x464): the whole volume is built in one launch;
