@@ -2,22 +2,24 @@
 """Benchmark of the plane-sweep hot path (BASELINE.json metric: cost-volume Gvoxels/s, ref views/s,
 % of HBM roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg4|cfg1|cfg3|fuse] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg4|cfg1|cfg3|cfg5|fuse] [--impl ours|reference]
 
-One "step" = one reference view of the workload: feature relayout (V launches), the fused
-warp+aggregate kernel (1 launch, the dominant one) and the fused softmax/regression kernel (1 launch).
-The CNN regulariser between the two is out of scope on both arms, so the logit volume is a synthetic
-input resident in HBM.  Under torchrun every rank processes its own K reference views (weak scaling by
-reference-view sharding, no collective on the data path); the only communication is the barrier and the
-max/sum joins of the timing.
+One "step" = one reference view of the workload: feature relayout (V launches), the fused warp+aggregate kernel (1 launch,
+the dominant one) and the fused softmax/regression kernel (1 launch).  The CNN regulariser between the two is out of scope
+on both arms, so the logit volume is a synthetic input resident in HBM.  Under torchrun every rank processes its own K
+reference views (weak scaling by reference-view sharding, no collective on the data path); the only communication is the
+barrier and the max/sum joins of the timing.
 
-`value` is measured with inputs resident in HBM; `e2e` runs the same step from pinned HOST buffers
-(features in, depth + confidence maps out) through the public API; `--impl reference` times the
-reference's CPU PyTorch path (the oracle restatement, which calls the same ATen ops) on the host cores.
+`value` is measured with inputs resident in HBM.  `e2e` runs the same step from pinned HOST buffers through the public API
+(deep3d_aerial_b200.pipeline.ViewPipeline): every rank walks a scene block in order and a reference view uploads the
+feature maps of the images that are not resident on its GPU yet (consecutive views share 4 of their 5 images), its
+cameras and hypotheses, and downloads its depth + confidence maps.  `--impl reference` times the reference's CPU PyTorch
+path (the oracle restatement, which calls the same ATen ops) on the host cores.
 
-The default workload, cfg2, is the configuration BASELINE.json's metric is quoted on; cfg3 (the AdaMVS 3-stage cascade
-per view) and fuse (the depth-map fusion consistency check) print the same kind of line for
-their own units of work.
+Workloads: cfg2 (default) is the configuration BASELINE.json's metric is quoted on; cfg4 its group-wise-correlation variant;
+cfg3 the AdaMVS 3-stage cascade per view at 1856 x 2752; cfg5 ONE scene block of --block-views reference views dealt to
+the ranks (strong scaling, views/s); fuse the depth-map fusion consistency check.  The default N = 1
+run appends short cfg4 / cfg3 / cfg5 measurements to its line as `extra_workloads` (--no-extra skips them).
 """
 from __future__ import annotations
 
@@ -56,6 +58,8 @@ def parse():
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (A/B; 0 = production)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="default run only: skip the short cfg4 / cfg3 / cfg5 measurements appended as extra_workloads")
     ap.add_argument("--debug-flat-hyps", action="store_true",
                     help="DIAGNOSTIC: all depth planes equal, so no footprint ever moves (isolates the re-fetch cost)")
     return ap.parse_args()
@@ -444,7 +448,7 @@ def run_ours(args):
 
     total_launches = int(shard.join_sum(launches))
     if rank != 0:
-        return 0
+        return None
     line = {
         "metric": "cost-volume Gvoxels/s", "value": value, "unit": "Gvoxel/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -465,8 +469,7 @@ def run_ours(args):
         line["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(wl)
-    print(json.dumps(line), flush=True)
-    return 0
+    return line
 
 
 # ------------------------------------------------------------------------------------- AdaMVS cascade (cfg3)
@@ -599,8 +602,79 @@ def run_cascade(args):
     dom_bytes = 4 * s["c"] * s["d"] * s["h"] * s["w"] + 4 * v * s["c"] * s["h"] * s["w"] + 4 * s["d"] * s["h"] * s["w"]
     achieved = dom_bytes / (kernel_ms["s%d_weighted_product" % (dom + 1)] * 1e-3) / 1e9
     total_launches = int(shard.join_sum(launches))
+
+    # ---- end to end: the reference views of a scene block in order; a view brings ONE image the device has not seen (the
+    # other four are the previous view's), so per view the feature pyramid of one image (three maps, 286 MB) goes
+    # host->device from pinned memory into a ring of V + 1 image slots -- on a copy stream, under the previous view's
+    # sweeps -- and the full-resolution depth + confidence maps come back device->host.
+    e2e = None
+    if not args.no_e2e:
+        n_e2e = max(3, args.steps)
+        pyramid = [torch.randn(s["c"], s["h"], s["w"], generator=g, dtype=torch.float32).pin_memory() for s in stages]
+        ring = [[torch.empty((v + 1, s["c"], s["h"], s["w"]), device=dev) for s in stages]]
+        for k, s in enumerate(stages):
+            ring[0][k][:v].copy_(s["feats"])
+        out_host = torch.empty((2, full_h, full_w), dtype=torch.float32).pin_memory()
+        copy_stream = torch.cuda.Stream()
+        arrived, consumed = torch.cuda.Event(), torch.cuda.Event()
+        consumed.record()
+        h2d = sum(t.numel() * 4 for t in pyramid)
+        sink = 0.0
+
+        def view(i):
+            """Views i uses ring slots i .. i+V-1 (mod V+1); the image of slot i+V (the next view's new one) is uploaded now."""
+            nonlocal sink
+            slot = (i + v) % (v + 1)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed)                   # the view that last read this slot is done with it
+                for k in range(3):
+                    ring[0][k][slot].copy_(pyramid[k], non_blocking=True)
+                arrived.record()
+            order = [(i + j) % (v + 1) for j in range(v)]
+            for k, s in enumerate(stages):
+                s["feats"] = ring[0][k][order]                     # (gathers the V maps: stands in for FeatureNet's outputs)
+            dep, conf = step()
+            consumed.record()
+            torch.cuda.current_stream().wait_event(arrived)        # the next view needs the image that just arrived
+            out_host[0].copy_(dep, non_blocking=True)
+            out_host[1].copy_(conf, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            sink += float(out_host[0, 0, 0]) + float(out_host[1, 0, 0])
+
+        view(0)
+        shard.barrier()
+        torch.cuda.synchronize()
+        t_host = time.perf_counter()
+        for i in range(1, 1 + n_e2e):
+            view(i)
+        torch.cuda.synchronize()
+        dt = shard.join_max(time.perf_counter() - t_host)
+        if not math.isfinite(sink):
+            raise SystemExit("bench.py: the cascade produced non-finite maps")
+        e2e = {"value": shard.join_sum(vox * n_e2e) / dt / 1e9, "unit": "Gvoxel/s", "ms_per_step": dt / n_e2e * 1e3,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host.numel() * 4, "steps": n_e2e,
+               "timer": "host wall clock", "stream": "one new image (feature pyramid of 3 maps) per reference view, "
+               "uploaded under the previous view's sweeps into a ring of V + 1 resident images"}
     if rank != 0:
-        return 0
+        return None
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import sweep_torch
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        s = stages[0]
+        feats = [s["feats"][i:i + 1].cpu() for i in range(v)]
+        proj = torch.from_numpy(rig.proj(4)).unsqueeze(0)
+        planes = 2
+        hy = torch.linspace(rig.dmin, rig.dmax, s["d"])[:planes].view(1, planes, 1, 1).repeat(1, 1, s["h"], s["w"])
+        wts = torch.rand(1, v - 1, s["h"], s["w"])
+        t_cpu = time.perf_counter()
+        sweep_torch.pair_mean_volumes(feats, proj, hy)
+        sweep_torch.weighted_product_volume(feats, proj, hy, [wts[:, i:i + 1] for i in range(v - 1)])
+        dt_cpu = time.perf_counter() - t_cpu
+        cpu = {"value": planes * s["h"] * s["w"] / dt_cpu / 1e9, "unit": "Gvoxel/s", "cores": cores, "kind": "port",
+               "sample": "stage 1 only (C=32 at 688x464): pair volumes + weighted product of %d of %d planes, torch %s CPU"
+                         % (planes, s["d"], torch.__version__)}
     line = {
         "metric": "cost-volume Gvoxels/s", "value": value, "unit": "Gvoxel/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -616,12 +690,11 @@ def run_cascade(args):
                      "algorithmic_bytes": dom_bytes, "peak_source": peak_src,
                      "whole_view_frac": sum(bytes_stage) / (ms_step * 1e-3) / 1e9 / peak},
         "clocks": clocks, "gpu_launches": total_launches,
-        "e2e": None, "cpu_baseline": None,
+        "e2e": e2e, "cpu_baseline": cpu,
         "note": "parity-test configuration measured for SURVEY.md 8d; the headline line is --workload cfg2",
     }
-    print(json.dumps(line), flush=True)
     float(out[0][0, 0])
-    return 0
+    return line
 
 
 # --------------------------------------------------------------------------- scene block across ranks (cfg5)
@@ -657,7 +730,7 @@ def run_scene_block(args):
     seconds = shard.join_max(rec.pop("seconds"))
     h2d = shard.join_sum(rec["h2d_bytes_per_step"] * len(mine)) / n_block
     if rank != 0:
-        return 0
+        return None
     value = n_block * vox / seconds / 1e9
     peak, peak_src = measured_peak()
     line = {
@@ -678,8 +751,7 @@ def run_scene_block(args):
         "cpu_baseline": None,
         "note": "BASELINE.json config 5 (views/s of a fixed block); the headline line is the default --workload cfg2",
     }
-    print(json.dumps(line), flush=True)
-    return 0
+    return line
 
 
 # ------------------------------------------------------------------------------------------------ row f3
@@ -773,7 +845,7 @@ def run_fuse(args):
                "timer": "host wall clock around submit/collect (fusion.FusionPipeline: copies overlap the kernel)"}
     total_launches = int(shard.join_sum(launches))
     if rank != 0:
-        return 0
+        return None
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         from oracle import fuse_np
@@ -802,8 +874,16 @@ def run_fuse(args):
         "clocks": clocks, "gpu_launches": total_launches, "e2e": e2e, "cpu_baseline": cpu,
         "note": "row f3 of SURVEY.md 8f; the headline line is --workload cfg2",
     }
-    print(json.dumps(line), flush=True)
-    return 0
+    return line
+
+
+def _brief(line):
+    """What the headline line keeps of another workload's line."""
+    keep = ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "ref_views_per_s", "kernel_ms", "roofline", "e2e",
+            "cpu_baseline", "gpu_launches", "note")
+    out = {k: line[k] for k in keep if k in line}
+    out["workload"] = line["config"]["workload"]
+    return out
 
 
 def main():
@@ -813,12 +893,36 @@ def main():
             args.workload = "cfg2"     # the reference arm is quoted on the headline configuration
         return run_reference(args)
     if args.workload == "cfg3":
-        return run_cascade(args)
-    if args.workload == "cfg5":
-        return run_scene_block(args)
-    if args.workload == "fuse":
-        return run_fuse(args)
-    return run_ours(args)
+        line = run_cascade(args)
+    elif args.workload == "cfg5":
+        line = run_scene_block(args)
+    elif args.workload == "fuse":
+        line = run_fuse(args)
+    else:
+        line = run_ours(args)
+        # the default run also records the other configurations of BASELINE.json, briefly, next to the headline (N = 1:
+        # the scaling runs are about the headline alone)
+        if line is not None and args.workload == "cfg2" and args.gpus == 1 and not args.no_extra and \
+                int(os.environ.get("WORLD_SIZE", "1")) == 1:
+            import copy
+            import torch
+            extra = {}
+            for name, fn, over in (("cfg4", run_ours, dict(workload="cfg4", steps=8, warmup=3, no_e2e=True)),
+                                   ("cfg3", run_cascade, dict(steps=5, warmup=3)),
+                                   ("cfg5", run_scene_block, dict(block_views=16, warmup=3))):
+                sub = copy.copy(args)
+                for k, val in over.items():
+                    setattr(sub, k, val)
+                sub.no_cpu_baseline = True if name != "cfg3" else args.no_cpu_baseline
+                torch.cuda.empty_cache()
+                try:
+                    extra[name] = _brief(fn(sub))
+                except Exception as exc:  # noqa: BLE001 -- an extra never costs the headline its line
+                    extra[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            line["extra_workloads"] = extra
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
 
 
 if __name__ == "__main__":
