@@ -38,7 +38,8 @@ __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y
 
 constexpr bool kQuadThreeCtas = true;   // <= 2 source views: 32 footprint registers, three CTAs per SM
 constexpr int kQuadPlanes = 4;       // planes per pass = planes per staged batch
-constexpr int kQuadBuffers = 4;      // staging ring
+constexpr int kQuadBuffers = 4;      // staging ring: batches
+constexpr int kQuadLag = kQuadBuffers / 2;   // a batch is drained while the batch `lag` later is computed
 __host__ __device__ constexpr int quad_dot_rows(int mode, int gs, int c) {
     return mode == D3D_AGG_PAIR_MEAN ? 4 : (gs == 4 ? c / 4 : c);
 }
@@ -419,7 +420,7 @@ sweep_quad_kernel(const SweepParams p) {
     int n = 0;
 #pragma unroll 1
     for (int b0 = d0; b0 < d1; b0 += KT, ++n) {
-        const bool draining = n >= 2;                // every batch but the last is full
+        const bool draining = n >= kQuadLag;         // every batch but the last is full
         if (draining) begin_drain();
 #pragma unroll
         for (int t = 0; t < KT; ++t) {
@@ -553,7 +554,7 @@ sweep_quad_kernel(const SweepParams p) {
         if (draining && slot_d == 0) dr -= TILE_RING;   // the drained slot was the last of the ring
     }
     // the sweep is over: the last two batches have nothing left to hide behind
-    for (int m = max(n - 2, 0); m < n; ++m) {
+    for (int m = max(n - kQuadLag, 0); m < n; ++m) {
         begin_drain();
         for (int k = min(KT, d1 - (d0 + m * KT)); k > 0; --k) drain_one();
         if (slot_d == 0) dr -= TILE_RING;
