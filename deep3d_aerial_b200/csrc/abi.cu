@@ -35,7 +35,6 @@ int sweep_base_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaSt
 int sweep_base_group_corr(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream);
 int sweep_base_weighted_product(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream);
 int sweep_base_pair_mean(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream);
-int sweep_fast_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_lean_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_quad_variance(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_ws_variance(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream);
@@ -152,9 +151,11 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
     };
     dim3 grid;
 
-    // variant 0: production kernel (lean formulation, 4 channels per lane where C <= 32, else 8);
-    //         3: the same with 8 channels per lane; 2: variant 0 with __fdiv_rn instead of the shared-reciprocal
-    //         division; 4 / 5: the earlier formulation (sweep_fast.cuh) with 4 / 8 channels per lane; 1: baseline.
+    // variant 0: production kernels (sweep_quad for 32- / 16-channel features, sweep_direct for 8, sweep_lean / sweep_base for
+    //            what those are not instantiated for);  1: baseline kernel (sweep_base) everywhere;  2: variant 0 with
+    //            __fdiv_rn instead of the shared-reciprocal division;  6: sweep_lean where variant 0 picks sweep_quad;
+    //            7: sweep_quad spelled out;  8 / 9: the TMA-prefetch experiments (sweep_ws / sweep_pre);  >= 16: A/B flag
+    //            bits of the production kernel (variant - 16 -> SweepParams.flags).
     // Shapes a kernel is not instantiated for fall through to the next one.
     int variant = a->variant;
     if (variant >= 16) { p.flags = variant - 16; variant = 0; }   // A/B switches of the production kernel
@@ -165,7 +166,7 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
         if (rc >= 0) return rc;
     }
     if (variant != 1 && a->mode == D3D_AGG_VARIANCE && nv <= 4) {
-        const bool want8 = (variant == 3 || variant == 5) && C % 8 == 0;
+        const bool want8 = false;                 // (8 channels per lane: only where 4 would need more than 8 lanes per pixel, C = 64)
         int fcpt = want8 ? 8 : 4;
         int fl2 = ilog2_exact(C / fcpt);
         if ((fl2 < 0 || fl2 > 3) && C % 8 == 0) { fcpt = 8; fl2 = ilog2_exact(C / 8); }
@@ -183,8 +184,7 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
                 rc = sweep_pre_variance(nv, p, grid, stream);
             if (rc < 0 && (variant == 0 || variant == 2 || variant == 7 || variant == 8 || variant == 9) && fcpt == 4 && (C == 32 || C == 16))
                 rc = sweep_quad_variance(nv, p, grid, stream, variant == 2);
-            if (rc < 0 && variant != 4 && variant != 5) rc = sweep_lean_variance(fcpt, nv, p, grid, stream, variant == 2);
-            if (rc < 0) rc = sweep_fast_variance(fcpt, nv, p, grid, stream, variant == 2);
+            if (rc < 0) rc = sweep_lean_variance(fcpt, nv, p, grid, stream, variant == 2);
             if (rc >= 0) return rc;
         }
     }

@@ -6,11 +6,11 @@
 //   carried from plane to plane (a footprint would serve ~3 planes of an 8-plane sweep), which keeps the
 //   kernel at ~64 registers -- 4x the resident warps of the cached formulation, and that is what hides the
 //   gather latency (sweep_base_kernel, 128 cached footprint registers per lane: 2.96 ms on the stage-3 shape).
-//   Each lane runs the projection chain of project_frac() (sweep_fast.cuh) for its own pixel -- with one lane
+//   Each lane runs the projection chain of project_frac() (sweep_util.cuh) for its own pixel -- with one lane
 //   per pixel nothing is computed twice -- and gathers the four 32-byte texels of every view with one
 //   LDG.256; corners outside the image are zero (loads predicated off), as grid_sample's zeros padding.
 #pragma once
-#include "sweep_fast.cuh"
+#include "sweep_util.cuh"
 
 namespace d3d {
 

@@ -1,6 +1,19 @@
-// Fused plane sweep, production kernel ("variant 0") -- instruction-lean formulation.
+// Fused plane sweep, two planes per projection pass (variant 6) -- the fall-back of sweep_quad.cuh for the shapes that
+// kernel is not instantiated for (C = 4, 8, 64; H*W not a multiple of the pixel tile).
 //
-// Same algorithm and decomposition as sweep_fast.cuh (read its header first).  The per-plane loop is re-stated
+// Decomposition (C = CPT*LPP channels; CPT = 4 or 8 channels per lane, LPP in {1,2,4,8} lanes per pixel):
+//   lane   = (pixel q of the warp, channel group cg of CPT channels);  LPP lanes share a pixel
+//   warp   = 32/LPP consecutive reference pixels x all channels
+//   group  = LPP warps = 32 consecutive pixels (one 128-byte row segment per output channel)
+//   CTA    = 8 warps = 8/LPP groups;  blockIdx.y = chunk of depth planes
+// Every thread walks its depth planes in order and keeps, per source view, the 2x2 texel footprint of its CPT channels
+// in registers; a footprint is re-fetched only when floor(ix), floor(iy) move.  The projection is computed ONCE per
+// (pixel, view, plane): the LPP lanes of a pixel split the source views (and, when there are more lanes than views, two
+// consecutive planes) and publish {fx, fy, fx*fy, key} through a per-warp double-buffered shared-memory table, one pass
+// ahead; bilinear interpolation as A + fx*B + fy*C + fx*fy*D in packed fp32x2; results leave through an XOR-swizzled
+// shared-memory tile as full 128-byte rows.  (The first kernel of this family, sweep_fast.cuh, is retired.)
+//
+// The per-plane loop is stated
 // so that nothing is re-derived per plane or per batch: the kernel is issue- and FP32-pipe-bound, and under the
 // 128-register cap (16 resident warps per SM) the compiler otherwise rematerialises addresses from threadIdx
 // (profiles/ncu_r1k.txt: 45 warp instructions per voxel, 74 per staged batch spent on pointer arithmetic).
@@ -27,7 +40,7 @@
 //         LDS.128 + STG.128 x CPT/4  one plane of an EARLIER batch leaves as 128-byte rows
 //     mbarrier arrive (split phase: the wait happens two batches later, when that batch is drained)
 #pragma once
-#include "sweep_fast.cuh"
+#include "sweep_util.cuh"
 
 namespace d3d {
 
@@ -73,7 +86,7 @@ __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
 }
 
 // Projection of one reference pixel onto one source view at one depth (operation order: see project_frac in
-// sweep_fast.cuh), returning {fx, fy, fx*fy, key} with the offset key described above.
+// sweep_util.cuh), returning {fx, fy, fx*fy, key} with the offset key described above.
 //   view_off = byte offset of the source view inside `feats`;  texel_bytes = C*4
 template <bool kIeeeDiv>
 __device__ __forceinline__ float4 project_off(float rx, float ry, float rz, float tx, float ty, float tz, float d,
@@ -166,7 +179,7 @@ __global__ void __launch_bounds__(256, (CPT == 4 ? 2 : 1)) sweep_lean_kernel(con
     }
     __syncthreads();
 
-    // ---- projection ownership (see sweep_fast.cuh) and per-lane constants
+    // ---- projection ownership (see the header) and per-lane constants
     const int po = (LPP >= NV) ? cg / NV : 0;
     const bool owner = (LPP >= NV) ? (cg < PB * NV) : true;
     float rx[KV], ry[KV], rz[KV], tx[KV], ty[KV], tz[KV];

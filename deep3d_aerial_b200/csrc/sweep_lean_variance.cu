@@ -1,6 +1,6 @@
-// Production sweep kernel (lean formulation) instantiations for D3D_AGG_VARIANCE, 1..4 source views:
+// sweep_lean_kernel instantiations for D3D_AGG_VARIANCE, 1..4 source views:
 //   4 channels per lane (16 resident warps per SM): C = 4, 8, 16, 32
-//   8 channels per lane ( 8 resident warps per SM): C = 8, 16, 32, 64
+//   8 channels per lane ( 8 resident warps per SM): C = 64 only (4 per lane would need 16 lanes per pixel)
 #include "sweep_lean.cuh"
 
 namespace d3d {
@@ -30,12 +30,7 @@ int sweep_lean_variance(int cpt, int nv, const SweepParams& p, dim3 grid, cudaSt
             default: return -1;
         }
     }
-    switch (p.lpp_log2) {
-        case 1: return by_views<8, 2>(nv, p, grid, stream, ieee);
-        case 2: return by_views<8, 4>(nv, p, grid, stream, ieee);
-        case 3: return by_views<8, 8>(nv, p, grid, stream, ieee);
-        default: return -1;
-    }
+    return p.lpp_log2 == 3 ? by_views<8, 8>(nv, p, grid, stream, ieee) : -1;
 }
 
 }  // namespace d3d

@@ -8,7 +8,7 @@
 //   * the 8 lanes of a pixel cover one PASS of 4 planes x 4 views with ONE projection chain each: lane cg
 //     projects view cg & 3 for the plane pair cg >> 2, the two planes packed in fp32x2 (FFMA2 / FADD2 / FMUL2,
 //     FADD2.RM for the floor); every operation is the same IEEE operation on each half, so the coordinates stay
-//     bit-identical to the reference chain (project_frac in sweep_fast.cuh);
+//     bit-identical to the reference chain (project_frac in sweep_util.cuh);
 //   * the published footprint key is just the floor corner as it falls out of the round-down adds
 //     ((y0 & 0xffff) << 16 | x0 & 0xffff, one PRMT); address arithmetic, the interior test and zeros padding
 //     moved into the re-fetch block (refetch_tok, sweep_refetch.cuh), which runs for ~9 % of the (view, plane)s;
@@ -299,7 +299,7 @@ sweep_quad_kernel(const SweepParams p) {
     };
 
     // Packed projection of the lane's view at two depths; every packed operation is the reference's IEEE
-    // operation on each half (see project_frac in sweep_fast.cuh for the order and why it is that order).
+    // operation on each half (see project_frac in sweep_util.cuh for the order and why it is that order).
     auto project2 = [&](int i, float2 d, float4& ea, float4& eb) {
         // (nvcc contracts __fmul2_rn + __fadd2_rn into one FFMA2, which would round once where the reference
         // rounds twice: every add that follows a multiply is a scalar __fadd_rn)
@@ -311,7 +311,7 @@ sweep_quad_kernel(const SweepParams p) {
         if (kIeeeDiv) {
             u = f2(__fdiv_rn(X.x, Z.x), __fdiv_rn(X.y, Z.y));
             v = f2(__fdiv_rn(Y.x, Z.x), __fdiv_rn(Y.y, Z.y));
-        } else {                                           // div2() of sweep_fast.cuh, both planes at once
+        } else {                                           // div2() of sweep_util.cuh, both planes at once
             float2 r;
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(Z.x));
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(Z.y));

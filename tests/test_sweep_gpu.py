@@ -295,14 +295,13 @@ CASES = [  # v, c, d, h, w, perpixel
 ]
 
 
-# kernel variants (include/d3d_sweep.h): 0 = production kernel, 1 = baseline kernel, 2 = production kernel
-# with __fdiv_rn instead of the shared-reciprocal division, 3 = production kernel with 8 channels per lane
-# 7 = the four-planes-per-pass kernel (sweep_quad.cuh), spelled out; 8 = the warp-specialised kernel (sweep_ws.cuh:
-# TMA-prefetched footprints, producer / consumer warps) wherever it is instantiated (32-channel features)
-# 9 = sweep_quad's formulation with TMA-prefetched footprints (sweep_pre.cuh);
-# 32 = sweep_quad's one-block re-fetch whatever the sweep length: the form long sweeps (D > 128) run, whose variance
-# volume keeps its footprints relative to the reference texel
-VARIANTS = [0, 1, 2, 3, 4, 5, 7, 8, 9, 32]
+# kernel variants (D3dCostVolumeArgs.variant, csrc/abi.cu): 0 = production kernels, 1 = baseline kernel (sweep_base),
+# 2 = production kernel with __fdiv_rn instead of the shared-reciprocal division, 6 = the two-planes-per-pass kernel
+# (sweep_lean) where variant 0 picks sweep_quad, 7 = sweep_quad spelled out, 8 / 9 = the TMA-prefetch experiments (sweep_ws:
+# warp-specialised; sweep_pre: sweep_quad with prefetched footprints) where they are instantiated (32-channel features),
+# 32 = sweep_quad's one-block re-fetch whatever the sweep length: the form long sweeps (D > 128) run, whose variance volume
+# keeps its footprints relative to the reference texel
+VARIANTS = [0, 1, 2, 6, 7, 8, 9, 32]
 
 
 @pytest.mark.parametrize("v,c,d,h,w,perpixel", CASES)
@@ -531,8 +530,8 @@ def test_texel_relayout_round_trip():
 
 # ------------------------------------------------------------------ (3) properties at full size
 @pytest.mark.parametrize("mode,kw", [(sweep.AGG_VARIANCE, {"variant": 0}), (sweep.AGG_VARIANCE, {"variant": 1}),
-                                     (sweep.AGG_VARIANCE, {"variant": 2}), (sweep.AGG_VARIANCE, {"variant": 3}),
-                                     (sweep.AGG_VARIANCE, {"variant": 4}), (sweep.AGG_VARIANCE, {"variant": 7}),
+                                     (sweep.AGG_VARIANCE, {"variant": 2}), (sweep.AGG_VARIANCE, {"variant": 6}),
+                                     (sweep.AGG_VARIANCE, {"variant": 7}),
                                      (sweep.AGG_VARIANCE, {"variant": 8}), (sweep.AGG_VARIANCE, {"variant": 9}),
                                      (sweep.AGG_GROUP_CORR, {"groups": 8})])
 def test_full_size_config_against_cuda_aten_on_plane_subsets(mode, kw):
