@@ -79,14 +79,17 @@ def measured_peak():
 
 
 def measured_traffic(wl):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_traffic.json);
-    None when there is no capture for this workload."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            rec = json.load(f).get(wl)
-        return None if not rec else int(rec["dram_bytes_read"]) + int(rec["dram_bytes_write"])
-    except (OSError, ValueError, KeyError):
-        return None
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r2_traffic.json, else
+    round 1's); None when there is no capture for this workload."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                rec = json.load(f).get(wl)
+            if rec:
+                return int(rec["dram_bytes_read"]) + int(rec["dram_bytes_write"])
+        except (OSError, ValueError, KeyError):
+            pass
+    return None
 
 
 class ClockSampler(threading.Thread):

@@ -143,9 +143,15 @@ __global__ void __launch_bounds__(kFuseThreads) consistency_fuse_kernel(const Fu
             ysd = (double)yi;
             if ((unsigned)xi < (unsigned)p.Ws && (unsigned)yi < (unsigned)p.Hs) {
                 at = at_used = (long long)yi * p.Ws + xi;
-            } else {                                                     // CuPy's wrap-around
-                at = wrap((long long)yi, p.Hs) * p.Ws + wrap((long long)xi, p.Ws);
-                at_used = wrap((long long)yi + (yi < 0), p.Hs) * p.Ws + wrap((long long)xi + (xi < 0), p.Ws);
+            } else {                                                     // CuPy's wrap-around (32-bit: |xi|, |yi| < 2^31 - 648)
+                auto wrap32 = [](int i, int n) { const int r = i % n; return r < 0 ? r + n : r; };
+                const int xw = wrap32(xi, p.Ws), yw = wrap32(yi, p.Hs);
+                at = (long long)yw * p.Ws + xw;
+                // the consumed pixel differs only for negative coordinates: one step towards zero, which the wrapped
+                // index follows (+1, and back to 0 past the last column / row)
+                const int xu = xi < 0 ? (xw + 1 == p.Ws ? 0 : xw + 1) : xw;
+                const int yu = yi < 0 ? (yw + 1 == p.Hs ? 0 : yw + 1) : yw;
+                at_used = (long long)yu * p.Ws + xu;
             }
         } else {                                                         // astype(int) is int64 upstream
             const long long xs = __double2ll_rz(fxs), ys = __double2ll_rz(fys);
