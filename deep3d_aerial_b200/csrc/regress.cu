@@ -205,6 +205,143 @@ __global__ void __launch_bounds__(256) regress_softmax_kernel(const RegressParam
     emit_next(p, pix, depth);
 }
 
+// The same, four consecutive pixels per thread: every logit (and per-pixel hypothesis) load is 16 bytes, a thread has
+// 8 x 16 bytes in flight per group of planes.  A pure stream lives on bytes in flight per SM; with 4-byte loads the kernel
+// above sits at 44 % of the HBM peak.  Needs H*W, the plane stride and the base addresses to be multiples of 4 floats;
+// uniform or per-pixel hypotheses (resized ones keep the scalar kernel: their taps are gathers).
+template <int HYPS, int PARTS>
+__global__ void __launch_bounds__(256) regress_softmax_vec_kernel(const RegressParams p) {
+    constexpr int QB = 256 / PARTS;                    // pixel quads per CTA
+    constexpr int G = 8;
+    __shared__ float part_state[PARTS > 1 ? PARTS : 1][6][QB * 4];
+    const int ql = threadIdx.x % QB, part = threadIdx.x / QB;
+    const long long quad_raw = (long long)blockIdx.x * QB + ql;
+    const bool live = quad_raw * 4 < p.HW;
+    if (PARTS == 1 && !live) return;
+    const int pix0 = live ? (int)(quad_raw * 4) : p.HW - 4;
+    const float* lg = p.logits + pix0;
+    const ResizeTap tap = {};
+
+    float m[4], s[4], sd[4], sk[4], sdd[4], dref[4];
+    int arg[4];
+    if (HYPS == D3D_HYPS_UNIFORM) {
+        const float d0 = __ldg(p.hyps);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dref[c] = d0;
+    } else {
+        const float4 d0 = ldg4(p.hyps + pix0);
+        dref[0] = d0.x; dref[1] = d0.y; dref[2] = d0.z; dref[3] = d0.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { m[c] = -INFINITY; s[c] = sd[c] = sk[c] = sdd[c] = 0.f; arg[c] = 0; }
+    const bool want_var = p.expvar != nullptr;
+    const int per = PARTS == 1 ? p.D : ((p.D + PARTS * G - 1) / (PARTS * G)) * G;
+    const int kbeg = part * per, kend = min(p.D, kbeg + per);
+    for (int k0 = kbeg; k0 < kend; k0 += G) {
+        float x[G][4], d[G][4];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const int k = k0 + j;
+            const bool ok = k < kend;
+            const float4 v = ok ? ldg4(lg + (size_t)k * p.stride_d) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            x[j][0] = v.x; x[j][1] = v.y; x[j][2] = v.z; x[j][3] = v.w;
+            if (HYPS == D3D_HYPS_UNIFORM) {
+                const float dk = ok ? __ldg(p.hyps + k) : dref[0];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) d[j][c] = dk;
+            } else {
+                const float4 w = ok ? ldg4(p.hyps + (size_t)k * p.HW + pix0) : make_float4(dref[0], dref[1], dref[2], dref[3]);
+                d[j][0] = w.x; d[j][1] = w.y; d[j][2] = w.z; d[j][3] = w.w;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float gm = x[0][c];
+#pragma unroll
+            for (int j = 1; j < G; ++j) gm = fmaxf(gm, x[j][c]);
+            if (gm > m[c]) {
+                const float r = expf(m[c] - gm);
+                s[c] *= r; sd[c] *= r; sk[c] *= r; sdd[c] *= r;
+#pragma unroll
+                for (int j = G - 1; j >= 0; --j)
+                    if (x[j][c] == gm) arg[c] = k0 + j;
+                m[c] = gm;
+            }
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const float e = expf(x[j][c] - m[c]);
+                const float dc = d[j][c] - dref[c];
+                s[c] += e;
+                sd[c] = fmaf(e, dc, sd[c]);
+                sk[c] = fmaf(e, (float)(k0 + j), sk[c]);
+                if (want_var) sdd[c] = fmaf(e * dc, dc, sdd[c]);
+            }
+        }
+    }
+    if (PARTS > 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int o = ql * 4 + c;
+            part_state[part][0][o] = m[c]; part_state[part][1][o] = s[c]; part_state[part][2][o] = sd[c];
+            part_state[part][3][o] = sk[c]; part_state[part][4][o] = sdd[c]; part_state[part][5][o] = __int_as_float(arg[c]);
+        }
+        __syncthreads();
+        if (part != 0 || !live) return;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int o = ql * 4 + c;
+#pragma unroll
+            for (int i = 1; i < PARTS; ++i) {
+                const float mi = part_state[i][0][o];
+                if (mi == -INFINITY) continue;
+                if (mi > m[c]) {
+                    const float r = expf(m[c] - mi);
+                    s[c] *= r; sd[c] *= r; sk[c] *= r; sdd[c] *= r;
+                    m[c] = mi;
+                    arg[c] = __float_as_int(part_state[i][5][o]);
+                }
+                const float r = expf(mi - m[c]);
+                s[c] = fmaf(part_state[i][1][o], r, s[c]);
+                sd[c] = fmaf(part_state[i][2][o], r, sd[c]);
+                sk[c] = fmaf(part_state[i][3][o], r, sk[c]);
+                sdd[c] = fmaf(part_state[i][4][o], r, sdd[c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int pix = pix0 + c;
+        const float inv = 1.f / s[c];
+        const float mean_c = sd[c] * inv;
+        const float depth = dref[c] + mean_c;
+        p.depth[pix] = depth;
+        float conf;
+        int idx;
+        if (p.conf_mode == D3D_CONF_MAX_PROB) {
+            conf = inv;
+            idx = arg[c];
+        } else {
+            idx = (int)(sk[c] * inv);
+            idx = max(0, min(idx, p.D - 1));
+            float w = 0.f;
+#pragma unroll
+            for (int j = -1; j <= 2; ++j) {
+                const int k = idx + j;
+                if (k >= 0 && k < p.D) w += expf(__ldg(p.logits + pix + (size_t)k * p.stride_d) - m[c]);
+            }
+            conf = w * inv;
+        }
+        p.conf[pix] = conf;
+        if (p.index) p.index[pix] = idx;
+        if (want_var) {
+            const float var = fmaxf(sdd[c] * inv - mean_c * mean_c, 0.f);
+            p.expvar[pix] = p.lamb * sqrtf(var);
+        }
+        emit_next(p, pix, depth);
+    }
+    (void)tap;
+}
+
 // ---- streaming un-normalised exp flavour ---------------------------------------------------------
 template <int HYPS>
 __global__ void __launch_bounds__(256) regress_rawexp_kernel(const RegressParams p) {
@@ -279,8 +416,15 @@ template <int HYPS>
 static int launch_regress(const RegressParams& p, int softmax_mode, cudaStream_t stream) {
     dim3 grid((p.HW + 255) / 256);
     if (softmax_mode == D3D_SOFTMAX_STABLE) {
+        // 16-byte loads over four pixels per thread where the layout allows it (uniform / per-pixel hypotheses)
+        const bool vec = HYPS != D3D_HYPS_RESIZED && (p.HW & 3) == 0 && (p.stride_d & 3) == 0 && p.HW >= 4 &&
+                         ((reinterpret_cast<uintptr_t>(p.logits) | reinterpret_cast<uintptr_t>(p.hyps)) & 15) == 0;
+        if (vec && p.D >= 32) regress_softmax_vec_kernel<HYPS == D3D_HYPS_RESIZED ? D3D_HYPS_UNIFORM : HYPS, 4>
+                <<<dim3((p.HW / 4 + 63) / 64), 256, 0, stream>>>(p);
+        else if (vec) regress_softmax_vec_kernel<HYPS == D3D_HYPS_RESIZED ? D3D_HYPS_UNIFORM : HYPS, 1>
+                <<<dim3((p.HW / 4 + 255) / 256), 256, 0, stream>>>(p);
         // long sweeps: four threads per pixel (a quarter of the planes each); short ones: one thread per pixel
-        if (p.D >= 32) regress_softmax_kernel<HYPS, 4><<<dim3((p.HW + 63) / 64), 256, 0, stream>>>(p);
+        else if (p.D >= 32) regress_softmax_kernel<HYPS, 4><<<dim3((p.HW + 63) / 64), 256, 0, stream>>>(p);
         else regress_softmax_kernel<HYPS, 1><<<grid, 256, 0, stream>>>(p);
     } else
         regress_rawexp_kernel<HYPS><<<grid, 256, 0, stream>>>(p);
