@@ -230,12 +230,32 @@ def run_reference(args):
     views = [feats[i:i + 1] for i in range(v)]
     projb = proj.unsqueeze(0)
 
+    # Where a reference checkout is present (this authoring container, or DEEP3D_REFERENCE_ROOT; never the GPU box), the
+    # variance workload runs the LIVE reference instead of the restatement: cas_mvsnet.DepthNet.forward (warp, variance,
+    # softmax, regression, confidence; cas_mvsnet.py:35-78) per chunk of 4 planes, its regulariser argument handing back
+    # the synthetic logits of the chunk.
+    kind, live_net = "port", None
+    if mode != "gwc":
+        try:
+            from oracle import ref_live
+            if ref_live.available():
+                live_net = ref_live.load().cas_mvsnet.DepthNet().eval()
+                kind = "reference"
+        except Exception:  # noqa: BLE001 -- no checkout, or it does not import here: the port is the same ATen calls
+            live_net = None
+
     def step(planes):
         sub = hyps[:planes].unsqueeze(0)
         if mode == "gwc":
             vol = sweep_torch.groupwise_correlation_volume(views, projb, sub, groups)
             float(vol[..., ::7, ::5].sum())
             sweep_torch.regress_maxprob(logits[:planes].unsqueeze(0), sub)
+        elif live_net is not None:
+            for d0 in range(0, planes, 4):
+                n = min(4, planes - d0)
+                chunk = logits[d0:d0 + n].view(1, 1, n, h, w)
+                out = live_net(views, projb, hyps[d0:d0 + n].view(1, n, 1, 1).expand(1, n, h, w), n, lambda vol, c=chunk: c)
+                float(out["depth"][0, 0, 0])
         else:
             sweep_torch.cpu_step_variance(views, projb, sub, logits[:planes].unsqueeze(0), plane_chunk=4)
 
@@ -259,7 +279,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "Gvoxel/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Gvoxel/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Gvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -14,7 +14,7 @@ import sys
 import types
 import warnings
 
-REF_ROOT = "/root/reference/mvs/mvs_cas"
+REF_ROOT = os.path.join(os.environ.get("DEEP3D_REFERENCE_ROOT", "/root/reference"), "mvs", "mvs_cas")
 
 
 def available() -> bool:
