@@ -140,6 +140,33 @@ def red_depthnet_forward(self, features, proj_matrices, depth_values, num_depth,
 STREAM_BATCH_PLANES = 16
 
 
+# Opt-in (row f1, second half): where the plane-at-a-time regulariser has the reference's layer list
+# (SliceCostRegNetRED, adamvs.py:403-427), only its two GRU cells carry state from plane to plane, and the two
+# recurrences do not feed each other's state.  So the stateless layers run ONCE over all D planes as a batch -- conv1
+# before GRU 1's walk, conv2 between the two walks, upconv1 + skip + ReLU + the output convolution after GRU 2's -- and
+# the soft-argmax is one launch over the whole logit volume.  Same layers, same weights, same per-plane operations;
+# cuDNN may pick another algorithm for a batch of D than for a batch of 1, so logits agree to rounding, not bit for bit.
+BATCH_STATELESS_CONVS = False
+_SLICE_REG_LAYERS = ("conv1", "conv_gru1", "conv2", "conv_gru2", "upconv1", "upconv2d")
+
+
+def batched_slice_regulariser(reg, volume, state1, state2):
+    """volume [D,C,h,w] (one batch item, plane-major) -> logits [D,1,H,W] through `reg`'s own layers (see above)."""
+    c1 = reg.conv1(volume)                                   # stateless: every plane at once
+    r1 = []
+    for k in range(volume.shape[0]):                         # recurrence 1
+        out, state1 = reg.conv_gru1(c1[k:k + 1], state1)
+        r1.append(out)
+    r1 = torch.cat(r1, 0)
+    c2 = reg.conv2(r1)                                       # stateless
+    r2 = []
+    for k in range(volume.shape[0]):                         # recurrence 2
+        out, state2 = reg.conv_gru2(c2[k:k + 1], state2)
+        r2.append(out)
+    up = F.relu(torch.add(reg.upconv1(torch.cat(r2, 0)), r1))   # adamvs.py:423-424
+    return reg.upconv2d(up)
+
+
 class _Stream:
     """Streaming soft-argmax accumulators of the plane-at-a-time models (adamvs.py:456-462, 514-529)."""
 
@@ -239,6 +266,17 @@ def ada_infer_forward(self, features, proj_matrices, depth_values, num_depth, co
                 "pair_confidence": pair_confidence, "pair_result": pair_results}
     similarity = _volume(features, proj_matrices, depth_values, sweep.AGG_WEIGHTED_PRODUCT, plane_major=True,
                          weights=weights, scenes=scenes)                                         # [B,D,C,h,w]
+    if BATCH_STATELESS_CONVS and all(hasattr(self.reg_fuse, n) for n in _SLICE_REG_LAYERS):
+        outs = []
+        for b in range(b_num):
+            logits = batched_slice_regulariser(self.reg_fuse, similarity[b], state1[b:b + 1], state2[b:b + 1])
+            outs.append(sweep.depth_regress(logits[:, 0], depth_values[b].contiguous(), softmax_mode=sweep.SOFTMAX_RAW_EXP,
+                                            want_index=False))
+        for d in range(num_depth):
+            pair_confidence.extend(resized)
+        return {"depth": torch.stack([o["depth"] for o in outs], 0),
+                "photometric_confidence": torch.stack([o["conf"] for o in outs], 0),
+                "pair_confidence": pair_confidence, "pair_result": pair_results}
     for d in range(num_depth):
         pair_confidence.extend(resized)
         reg_cost, state1, state2 = self.reg_fuse(similarity[:, d], state1, state2)               # :512

@@ -190,3 +190,57 @@ def fusion_scene(num_src=4, height=96, width=128, seed=0, focal=None, z_mean=500
     prob = rng.random((rig.height, rig.width)).astype(np.float32)
     d, n, k, e = views[0]
     return {"ref": (d, n, k, e, prob), "src": views[1:]}
+
+
+class _GruCell(torch.nn.Module):
+    """A convolutional GRU cell of the shape the reference's recurrent regularisers use (module.py:5-50: one 3x3
+    convolution for the reset / update gates, one for the candidate, `u*h + (1-u)*tanh(.)`).  Written from that
+    description for the synthetic regulariser below; weights are seeded, not trained."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.gates = torch.nn.Conv2d(2 * channels, 2 * channels, 3, padding=1)
+        self.cand = torch.nn.Conv2d(2 * channels, channels, 3, padding=1)
+
+    def forward(self, x, h):
+        r, u = torch.sigmoid(self.gates(torch.cat((x, h), 1))).chunk(2, 1)
+        c = torch.tanh(self.cand(torch.cat((x, r * h), 1)))
+        out = u * h + (1 - u) * c
+        return out, out
+
+
+class _ConvRelu(torch.nn.Module):
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(cin, cout, 3, stride=stride, padding=1, bias=False)
+
+    def forward(self, x):
+        return torch.nn.functional.relu(self.conv(x))
+
+
+class SliceRegulariser(torch.nn.Module):
+    """A seeded stand-in with the LAYER LIST of the reference's plane-at-a-time regulariser (SliceCostRegNetRED,
+    adamvs.py:403-427: ConvReLU -> ConvGRU -> strided ConvReLU -> ConvGRU -> transposed conv + skip + ReLU -> output
+    conv, x2 up-sampling when `up`), under the attribute names the reference uses, so that timing and batching code
+    sees what it would see in production.  `forward(cost [B,C,h,w], state1, state2) -> (logit [B,1,H,W], state1, state2)`."""
+
+    def __init__(self, in_channels, up=True, base=8, seed=0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.conv1 = _ConvRelu(in_channels, base, 1)
+        self.conv_gru1 = _GruCell(base)
+        self.conv2 = _ConvRelu(base, 2 * base, 2)
+        self.conv_gru2 = _GruCell(2 * base)
+        self.upconv1 = torch.nn.ConvTranspose2d(2 * base, base, 3, stride=2, padding=1, output_padding=1)
+        self.upconv2d = (torch.nn.ConvTranspose2d(base, 1, 3, stride=2, padding=1, output_padding=1) if up
+                         else torch.nn.Conv2d(base, 1, 3, padding=1))
+        with torch.no_grad():
+            for prm in self.parameters():
+                prm.copy_(0.15 * torch.randn(prm.shape, generator=g))
+
+    def forward(self, cost, state1, state2):
+        c1 = self.conv1(cost)
+        r1, state1 = self.conv_gru1(c1, state1)
+        r2, state2 = self.conv_gru2(self.conv2(r1), state2)
+        up = torch.nn.functional.relu(self.upconv1(r2) + r1)
+        return self.upconv2d(up), state1, state2

@@ -7,6 +7,8 @@
 Tolerances are north_star's: cost volumes <= 1e-4 relative (norm-wise: max|a-b| / max|b|, SURVEY.md §7
 hard part 2), regressed depth <= 1e-3 relative, arg-max plane agreement >= 99.9 %.
 """
+import types
+
 import pytest
 import torch
 
@@ -202,6 +204,26 @@ class _RedLike(torch.nn.Module):
         logit = -2.0 * x.mean(1, keepdim=True) + s1.mean(1, keepdim=True) + up(s2.mean(1, keepdim=True), scale_factor=2) \
             + up(s4.mean(1, keepdim=True), scale_factor=8)
         return logit, s1, s2, s3, s4
+
+
+@pytest.mark.parametrize("in_up", [True, False])
+def test_batched_stateless_convs_match_the_plane_at_a_time_loop(in_up, monkeypatch):
+    """depthnets.BATCH_STATELESS_CONVS (row f1): a regulariser with the reference's layer list (SliceCostRegNetRED,
+    adamvs.py:403-427; here synth.SliceRegulariser, seeded) run with its stateless convolutions batched over all planes
+    and one soft-argmax launch over the whole logit volume, against the plane-at-a-time loop of adamvs.py:492-529."""
+    v, c, d, h, w = 4, 16, 12, 32, 40
+    _, proj, feats, hyps = _scene(v, c, d, h, w, seed=31, smooth=True)
+    views = _cuda_views(feats)
+    hy = hyps.view(1, d, 1, 1).expand(1, d, h, w).contiguous().to(DEV)
+    conf = [torch.rand(1, 1, h, w, generator=torch.Generator().manual_seed(k)).to(DEV) for k in range(v - 1)]
+    net = types.SimpleNamespace(in_up=in_up, reg=None, reg_fuse=synth.SliceRegulariser(c, up=in_up, seed=3).to(DEV).eval())
+    monkeypatch.setattr(depthnets, "BATCH_STATELESS_CONVS", False)
+    want = depthnets.ada_infer_forward(net, views, proj.to(DEV), hy, d, confidence_map=conf)
+    monkeypatch.setattr(depthnets, "BATCH_STATELESS_CONVS", True)
+    got = depthnets.ada_infer_forward(net, views, proj.to(DEV), hy, d, confidence_map=conf)
+    assert _depth_err(got["depth"], want["depth"]) < 1e-5
+    assert float((got["photometric_confidence"] - want["photometric_confidence"]).abs().max()) < 1e-5
+    assert len(got["pair_confidence"]) == len(want["pair_confidence"])
 
 
 def test_red_plane_loop_graph_matches_eager():
