@@ -370,6 +370,21 @@ def test_group_corr_matches_oracle(groups):
     assert rel_norm_err(got, want) < VOL_TOL
 
 
+@pytest.mark.parametrize("v,groups,perpixel,d", [(3, 8, True, 9), (4, 2, True, 6), (2, 4, False, 13), (5, 8, False, 24),
+                                                 (5, 32, True, 7)])
+@pytest.mark.parametrize("variant", [0, 48])
+def test_group_corr_dot_cache_and_coefficient_cache_agree_with_the_oracle(v, groups, perpixel, d, variant):
+    """Group-wise correlation of 32-channel features: variant 0 keeps cached corner DOT PRODUCTS where a group spans a
+    lane's 4 channels or more (groups <= 8), variant 48 the 16 interpolation coefficients; per-pixel hypotheses, 1-4
+    source views, ragged last batches.  (The oracle's group-wise volume is a restatement by analogy with adamvs.py:473:
+    parity unpinned by the reference for this mode.)"""
+    _, proj, feats, hyps = _scene(v, 32, d, 48, 40, seed=40 + v, perpixel=perpixel)
+    want = sweep_torch.groupwise_correlation_volume(_views(feats), proj, hyps, groups)[0]
+    got = _ours_volume(feats, proj, hyps, sweep.AGG_GROUP_CORR, groups=groups, variant=variant)
+    assert got.shape == want.shape
+    assert rel_norm_err(got, want) < VOL_TOL
+
+
 def test_group_corr_wide_groups_lane_reduction():
     _, proj, feats, hyps = _scene(7, 32, 6, 20, 28, seed=6)      # 4 channels per lane, groups of 16 span 4 lanes
     want = sweep_torch.groupwise_correlation_volume(_views(feats), proj, hyps, 2)[0]
