@@ -141,6 +141,32 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_vec_kernel(const float* __re
     }
 }
 
+// Warp-tile version (round 2): a warp moves 32 pixels x C channels.  It reads C rows of 32 consecutive pixels (one
+// 128-byte line per load instruction), parks them in a padded shared-memory tile and writes the 32*C output floats as C
+// store instructions of 32 CONSECUTIVE floats each (= 32/C whole texels): every global access of the kernel is a full
+// 128-byte line.  The register-transpose kernel above writes 32-byte segments at a 128-byte stride (2.3 TB/s class
+// stores, r1_microbench.txt): 25.6 us per 32-channel 688x464 map = 3.2 TB/s.
+template <int C>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_tile_kernel(const float* __restrict__ in, float* __restrict__ out, int HW) {
+    __shared__ float tile[8][C][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long pix0 = ((long long)blockIdx.x * 8 + warp) * 32;
+    if (pix0 >= HW) return;
+    const int n = min(32, (int)(HW - pix0));               // pixels of this tile (ragged tail)
+    float v[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = lane < n ? __ldg(in + (size_t)c * HW + pix0 + lane) : 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) tile[warp][c][lane] = v[c];
+    __syncwarp();
+    float* o = out + (size_t)pix0 * C;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        const int f = j * 32 + lane;                       // flat index inside the tile's output: pixel f / C, channel f % C
+        if (f < n * C) o[f] = tile[warp][f % C][f / C];
+    }
+}
+
 }  // namespace d3d
 
 using namespace d3d;
@@ -273,6 +299,15 @@ extern "C" int d3d_nchw_to_nhwc(const float* in, float* out, int32_t channels, i
                     width);
     long long hw = (long long)height * width;
     if (hw > INT32_MAX) return fail(D3D_ERR_UNSUPPORTED, "d3d_nchw_to_nhwc: H*W exceeds 2^31-1");
+    if (channels == 32 || channels == 16 || channels == 8) {       // the reference's feature widths: warp-tile version
+        const unsigned blocks = (unsigned)((hw + 255) / 256);
+        cudaStream_t st = (cudaStream_t)cuda_stream;
+        if (channels == 32) nchw_to_nhwc_tile_kernel<32><<<blocks, 256, 0, st>>>(in, out, (int)hw);
+        else if (channels == 16) nchw_to_nhwc_tile_kernel<16><<<blocks, 256, 0, st>>>(in, out, (int)hw);
+        else nchw_to_nhwc_tile_kernel<8><<<blocks, 256, 0, st>>>(in, out, (int)hw);
+        count_launch();
+        return check_launch("nchw_to_nhwc_tile_kernel");
+    }
     if (channels % 8 == 0 && hw % 4 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
         const dim3 grid((unsigned)((hw / 4 + 255) / 256), (unsigned)(channels / 8));
         nchw_to_nhwc_vec_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(in, out, channels, (int)hw);
