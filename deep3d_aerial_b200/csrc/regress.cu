@@ -209,10 +209,9 @@ __global__ void __launch_bounds__(256) regress_softmax_kernel(const RegressParam
 // 8 x 16 bytes in flight per group of planes.  A pure stream lives on bytes in flight per SM; with 4-byte loads the kernel
 // above sits at 44 % of the HBM peak.  Needs H*W, the plane stride and the base addresses to be multiples of 4 floats;
 // uniform or per-pixel hypotheses (resized ones keep the scalar kernel: their taps are gathers).
-template <int HYPS, int PARTS>
-__global__ void __launch_bounds__(256) regress_softmax_vec_kernel(const RegressParams p) {
+template <int HYPS, int PARTS, int G = 8>
+__global__ void __launch_bounds__(256, 2) regress_softmax_vec_kernel(const RegressParams p) {
     constexpr int QB = 256 / PARTS;                    // pixel quads per CTA
-    constexpr int G = 8;
     __shared__ float part_state[PARTS > 1 ? PARTS : 1][6][QB * 4];
     const int ql = threadIdx.x % QB, part = threadIdx.x / QB;
     const long long quad_raw = (long long)blockIdx.x * QB + ql;
@@ -419,7 +418,10 @@ static int launch_regress(const RegressParams& p, int softmax_mode, cudaStream_t
         // 16-byte loads over four pixels per thread where the layout allows it (uniform / per-pixel hypotheses)
         const bool vec = HYPS != D3D_HYPS_RESIZED && (p.HW & 3) == 0 && (p.stride_d & 3) == 0 && p.HW >= 4 &&
                          ((reinterpret_cast<uintptr_t>(p.logits) | reinterpret_cast<uintptr_t>(p.hyps)) & 15) == 0;
-        if (vec && p.D >= 32) regress_softmax_vec_kernel<HYPS == D3D_HYPS_RESIZED ? D3D_HYPS_UNIFORM : HYPS, 4>
+        // (uniform hypotheses leave registers for 12 planes in flight per thread: 96 KB of loads outstanding per SM)
+        if (vec && p.D >= 96 && HYPS == D3D_HYPS_UNIFORM) regress_softmax_vec_kernel<D3D_HYPS_UNIFORM, 4, 12>
+                <<<dim3((p.HW / 4 + 63) / 64), 256, 0, stream>>>(p);
+        else if (vec && p.D >= 32) regress_softmax_vec_kernel<HYPS == D3D_HYPS_RESIZED ? D3D_HYPS_UNIFORM : HYPS, 4>
                 <<<dim3((p.HW / 4 + 63) / 64), 256, 0, stream>>>(p);
         else if (vec) regress_softmax_vec_kernel<HYPS == D3D_HYPS_RESIZED ? D3D_HYPS_UNIFORM : HYPS, 1>
                 <<<dim3((p.HW / 4 + 255) / 256), 256, 0, stream>>>(p);
