@@ -209,8 +209,12 @@ __global__ void __launch_bounds__(256) regress_softmax_kernel(const RegressParam
 // 8 x 16 bytes in flight per group of planes.  A pure stream lives on bytes in flight per SM; with 4-byte loads the kernel
 // above sits at 44 % of the HBM peak.  Needs H*W, the plane stride and the base addresses to be multiples of 4 floats;
 // uniform or per-pixel hypotheses (resized ones keep the scalar kernel: their taps are gathers).
-template <int HYPS, int PARTS, int G = 8>
-__global__ void __launch_bounds__(256, 2) regress_softmax_vec_kernel(const RegressParams p) {
+// kWin4 / kVar: the sums only the window-4 confidence (sum p*k) and exp_variance (sum p*d^2) need are compiled out
+// otherwise.  exp() is ex2.approx(x * log2 e): every argument is <= 0 after the max subtraction and the terms that matter
+// have small |x|, where its error is ~3e-7 relative -- three orders below the depth tolerance; the accurate expf() cost
+// more instructions than the rest of the element put together (profiles: 63 % issue utilisation at 55 % of the HBM peak).
+template <int HYPS, int PARTS, int G, bool kWin4, bool kVar>
+__global__ void __launch_bounds__(256, (G == 8 && HYPS == D3D_HYPS_UNIFORM) ? 3 : 2) regress_softmax_vec_kernel(const RegressParams p) {
     constexpr int QB = 256 / PARTS;                    // pixel quads per CTA
     __shared__ float part_state[PARTS > 1 ? PARTS : 1][6][QB * 4];
     const int ql = threadIdx.x % QB, part = threadIdx.x / QB;
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(256, 2) regress_softmax_vec_kernel(const Regre
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) { m[c] = -INFINITY; s[c] = sd[c] = sk[c] = sdd[c] = 0.f; arg[c] = 0; }
-    const bool want_var = p.expvar != nullptr;
+    constexpr bool want_var = kVar;
     const int per = PARTS == 1 ? p.D : ((p.D + PARTS * G - 1) / (PARTS * G)) * G;
     const int kbeg = part * per, kend = min(p.D, kbeg + per);
     for (int k0 = kbeg; k0 < kend; k0 += G) {
@@ -259,20 +263,21 @@ __global__ void __launch_bounds__(256, 2) regress_softmax_vec_kernel(const Regre
 #pragma unroll
             for (int j = 1; j < G; ++j) gm = fmaxf(gm, x[j][c]);
             if (gm > m[c]) {
-                const float r = expf(m[c] - gm);
+                const float r = __expf(m[c] - gm);
                 s[c] *= r; sd[c] *= r; sk[c] *= r; sdd[c] *= r;
 #pragma unroll
                 for (int j = G - 1; j >= 0; --j)
                     if (x[j][c] == gm) arg[c] = k0 + j;
                 m[c] = gm;
             }
+            const float kf = (float)k0;
 #pragma unroll
             for (int j = 0; j < G; ++j) {
-                const float e = expf(x[j][c] - m[c]);
+                const float e = __expf(x[j][c] - m[c]);
                 const float dc = d[j][c] - dref[c];
                 s[c] += e;
                 sd[c] = fmaf(e, dc, sd[c]);
-                sk[c] = fmaf(e, (float)(k0 + j), sk[c]);
+                if (kWin4) sk[c] = fmaf(e, kf + (float)j, sk[c]);
                 if (want_var) sdd[c] = fmaf(e * dc, dc, sdd[c]);
             }
         }
@@ -294,12 +299,12 @@ __global__ void __launch_bounds__(256, 2) regress_softmax_vec_kernel(const Regre
                 const float mi = part_state[i][0][o];
                 if (mi == -INFINITY) continue;
                 if (mi > m[c]) {
-                    const float r = expf(m[c] - mi);
+                    const float r = __expf(m[c] - mi);
                     s[c] *= r; sd[c] *= r; sk[c] *= r; sdd[c] *= r;
                     m[c] = mi;
                     arg[c] = __float_as_int(part_state[i][5][o]);
                 }
-                const float r = expf(mi - m[c]);
+                const float r = __expf(mi - m[c]);
                 s[c] = fmaf(part_state[i][1][o], r, s[c]);
                 sd[c] = fmaf(part_state[i][2][o], r, sd[c]);
                 sk[c] = fmaf(part_state[i][3][o], r, sk[c]);
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(256, 2) regress_softmax_vec_kernel(const Regre
         p.depth[pix] = depth;
         float conf;
         int idx;
-        if (p.conf_mode == D3D_CONF_MAX_PROB) {
+        if (!kWin4) {
             conf = inv;
             idx = arg[c];
         } else {
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(256, 2) regress_softmax_vec_kernel(const Regre
 #pragma unroll
             for (int j = -1; j <= 2; ++j) {
                 const int k = idx + j;
-                if (k >= 0 && k < p.D) w += expf(__ldg(p.logits + pix + (size_t)k * p.stride_d) - m[c]);
+                if (k >= 0 && k < p.D) w += __expf(__ldg(p.logits + pix + (size_t)k * p.stride_d) - m[c]);
             }
             conf = w * inv;
         }
@@ -418,13 +423,23 @@ static int launch_regress(const RegressParams& p, int softmax_mode, cudaStream_t
         // 16-byte loads over four pixels per thread where the layout allows it (uniform / per-pixel hypotheses)
         const bool vec = HYPS != D3D_HYPS_RESIZED && (p.HW & 3) == 0 && (p.stride_d & 3) == 0 && p.HW >= 4 &&
                          ((reinterpret_cast<uintptr_t>(p.logits) | reinterpret_cast<uintptr_t>(p.hyps)) & 15) == 0;
-        // (uniform hypotheses leave registers for 12 planes in flight per thread: 96 KB of loads outstanding per SM)
-        if (vec && p.D >= 96 && HYPS == D3D_HYPS_UNIFORM) regress_softmax_vec_kernel<D3D_HYPS_UNIFORM, 4, 12>
-                <<<dim3((p.HW / 4 + 63) / 64), 256, 0, stream>>>(p);
-        else if (vec && p.D >= 32) regress_softmax_vec_kernel<HYPS == D3D_HYPS_RESIZED ? D3D_HYPS_UNIFORM : HYPS, 4>
-                <<<dim3((p.HW / 4 + 63) / 64), 256, 0, stream>>>(p);
-        else if (vec) regress_softmax_vec_kernel<HYPS == D3D_HYPS_RESIZED ? D3D_HYPS_UNIFORM : HYPS, 1>
-                <<<dim3((p.HW / 4 + 255) / 256), 256, 0, stream>>>(p);
+        if (vec) {
+            constexpr int VH = HYPS == D3D_HYPS_RESIZED ? D3D_HYPS_UNIFORM : HYPS;
+            const bool win4 = p.conf_mode != D3D_CONF_MAX_PROB, var = p.expvar != nullptr;
+            const dim3 g4((p.HW / 4 + 63) / 64), g1((p.HW / 4 + 255) / 256);
+            // (uniform hypotheses fit 85 registers: three CTAs per SM, 8 x 16 bytes in flight per thread = 98 KB of loads
+            // outstanding per SM -- 0.108 ms at cfg2; 12 planes in flight at two CTAs per SM: 0.115 ms; four CTAs spill: 0.161 ms)
+#define D3D_VEC(PARTS, G, GRID)                                                                              \
+            do {                                                                                             \
+                if (win4 && var) regress_softmax_vec_kernel<VH, PARTS, G, true, true><<<GRID, 256, 0, stream>>>(p);        \
+                else if (win4) regress_softmax_vec_kernel<VH, PARTS, G, true, false><<<GRID, 256, 0, stream>>>(p);         \
+                else if (var) regress_softmax_vec_kernel<VH, PARTS, G, false, true><<<GRID, 256, 0, stream>>>(p);          \
+                else regress_softmax_vec_kernel<VH, PARTS, G, false, false><<<GRID, 256, 0, stream>>>(p);                  \
+            } while (0)
+            if (p.D >= 32) D3D_VEC(4, 8, g4);
+            else D3D_VEC(1, 8, g1);
+#undef D3D_VEC
+        }
         // long sweeps: four threads per pixel (a quarter of the planes each); short ones: one thread per pixel
         else if (p.D >= 32) regress_softmax_kernel<HYPS, 4><<<dim3((p.HW + 63) / 64), 256, 0, stream>>>(p);
         else regress_softmax_kernel<HYPS, 1><<<grid, 256, 0, stream>>>(p);
