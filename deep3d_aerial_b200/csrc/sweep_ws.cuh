@@ -1,34 +1,38 @@
-// Fused plane sweep, warp-specialised form for 32-channel features (round 2 production kernel for the long sweeps).
+// Fused plane sweep, warp-specialised form for 32-channel features (round-2 experiment, `variant` 8; NOT the default:
+// 6.54 ms at cfg2 against sweep_quad's 5.37 ms -- DESIGN.md 2.7 has the account).
 //
-// Why: profiles/ncu_r1n.txt -- in sweep_quad_kernel the FP32 arithmetic of the volume is 46 of the ~120 warp
-// instructions a warp issues per plane; the rest is the projection chain, the footprint-key tests, the re-fetch
-// (address arithmetic + 4 global loads whose latency the warp eats: 19 % of all stall samples), the drain of the
-// staged rows and the pointer upkeep around them, and with 122 registers only 4 warps per scheduler hide it.
-// Here the CTA is split by role (setmaxnreg moves the registers to where the footprints live):
+// Why it was built: profiles/ncu_r1n.txt -- in sweep_quad_kernel the FP32 arithmetic of the volume is 46 of the ~120 warp
+// instructions a warp issues per plane; the rest is the projection chain, the footprint-key tests, the re-fetch (address
+// arithmetic + 4 global loads whose latency the warp eats: 19 % of all stall samples), the drain of the staged rows and
+// the pointer upkeep around them, and with 122 registers only 4 warps per scheduler hide it.  Here the CTA is split by
+// role (setmaxnreg moves the registers to where the footprints live):
 //
-//   * 8 CONSUMER warps (104 registers) own the register-resident footprint cache (lane = pixel q of the warp x
-//     group cg of 4 channels, as in sweep_quad.cuh) and do nothing but: 4 LDS.128 of the plane's table entries,
-//     one test "did anything move", the packed FFMA2 arithmetic, 4 STS.32 into the staging tile.  A moved
-//     footprint is picked up from a shared-memory SLOT (4 LDS.128 + the packed rebuild): no address arithmetic,
-//     no global load, no long-scoreboard stall.
-//   * 4 PRODUCER warps (32 registers), one lane per (pixel, source view) STREAM of 8 pixels: the packed
-//     projection chain (two planes per FFMA2/FADD2, operation order of the reference, see project2 in
-//     sweep_quad.cuh), the move test against the stream's previous floor corner (lane-local), and for every moved
-//     footprint ONE warp-wide cp.async (32 lanes x 16 bytes = 4 corners x 32 channels; corners outside the image
-//     are written as zeros = grid_sample's zeros padding) into a slot of the pass's region, a whole pass (4
-//     planes) ahead of its use.  The table entry {fx, fy, fx*fy, info} tells the consumer where the slot is.
-//     When a region is full (14 slots per producer warp and pass; the cfg2 rig averages 8 moves) the entry
-//     carries the floor corner instead and the consumer fetches from global memory itself (consume_ws, rare).
-//     The same warps drain the staged rows (LDS.128 -> 128-byte STG.128 rows, L1::no_allocate).
+//   * 8 CONSUMER warps (104 registers) own the register-resident footprint cache (lane = pixel q of the warp x group cg
+//     of 4 channels, as in sweep_quad.cuh) and do nothing but: 4 LDS.128 of the plane's table entries, one test "did
+//     anything move", the packed FFMA2 arithmetic, 4 STS.32 into the staging tile -- 56 instructions per plane, 42 of them
+//     arithmetic.  A moved footprint is picked up from a shared-memory SLOT (4 LDS.128 + the packed rebuild,
+//     consume_ws_shift): no address arithmetic, no global load, no long-scoreboard stall.
+//   * 4 PRODUCER warps (32 registers), one lane per (pixel, source view) STREAM of 8 pixels: the packed projection chain
+//     (two planes per FFMA2/FADD2, operation order of the reference, see project2 in sweep_quad.cuh), the move test
+//     against the stream's previous floor corner (lane-local), and for every moved footprint ONE
+//     cp.async.bulk.tensor.4d -- the 2 x 2 x 32-channel box of the texel tensor at (x0, y0, view), texels outside the
+//     image arriving as zeros (the tensor map's out-of-bounds fill = grid_sample's zeros padding) -- into a slot of the
+//     pass's region, a whole pass (4 planes) ahead of its use.  The table entry {fx, fy, fx*fy, info} tells the consumer
+//     where the slot is.  When a region is full (14 slots per producer warp and pass; the cfg2 rig averages 8 moves)
+//     the entry carries the floor corner instead and the consumer fetches from global memory itself (rare).  The same
+//     warps drain the staged rows (LDS.128 -> 128-byte STG.128 rows, L1::no_allocate), after the pass is produced, so
+//     the drain overlaps the flight time of the pass's copies.
 //
 // Synchronisation is all mbarriers (no bar.sync in the loop), two-deep rings:
-//     tfull[pw][2]  producer warp pw -> its two consumer warps: table + slots of a pass are complete
-//                   (32 cp.async.mbarrier.arrive.noinc, which fire when the lane's copies have landed, + 1 arrive
-//                   that releases the table stores)
+//     tfull[pw][2]  producer warp pw -> its two consumer warps: table + slots of a pass are complete (one arrive that
+//                   releases the table stores + the bytes of the pass's copies, expect_tx / complete_tx)
 //     tempty[pw][2] the two consumer warps -> producer: pass consumed, table + slot region may be overwritten
 //     sfull[2]      8 consumer warps -> producers: a batch of 4 planes is staged
 //     sempty[2]     4 producer warps -> consumers: the batch has left, the staging buffer is free
 // The producer runs one pass ahead: produce(n + 1) happens while the consumers compute pass n.
+//
+// What it measured (profiles/ncu_r2_ws_variant8.txt): the consumers run at ~85 % FP32-pipe utilisation when fed, but wait
+// on tfull for 21-32 % of their time: a producer warp needs ~390 instructions per pass and gets one issue slot in six.
 //
 // Variance volume: the reference texel is subtracted from every footprint's A at rebuild time (variance is shift
 // invariant), so the reference view contributes nothing to sum and sum of squares: one packed add per channel pair
