@@ -133,7 +133,11 @@ sweep_quad_kernel(const SweepParams p) {
     constexpr int JPL = 8 / LPP;                           // projection chains a lane runs per pass
     constexpr int NVL = JPL > 1 ? JPL / 2 : 1;             // distinct views among them
     constexpr int KT = kQuadPlanes, NBUF = kQuadBuffers;
-    constexpr int VS = NV <= 2 ? 2 : 4;                    // view slots of the table
+    // Table layout.  LPP = 8 (kRec): one 64-byte RECORD per pixel and plane, {key[4 views] | fx[4] | fy[4] | fx*fy[4]} -- the
+    // four values of a kind land in adjacent registers with one LDS.128 (what packs the correlation modes' arithmetic over
+    // view pairs).  Otherwise: one 16-byte entry {fx, fy, fx*fy, key} per (view, pixel).
+    constexpr bool kRec = LPP == 8;
+    constexpr int VS = kRec ? 4 : (NV <= 2 ? 2 : 4);       // view slots of the table
     constexpr unsigned GEO_PLANE = VS * PPW * 16;          // bytes: one plane's table of one warp
     constexpr unsigned GEO_BUF = KT * GEO_PLANE;
     // rows of a staged plane: the channels, or -- with the dot-product cache -- only the rows the mode writes (8 groups of
@@ -224,10 +228,11 @@ sweep_quad_kernel(const SweepParams p) {
     const unsigned row_bytes = (unsigned)p.W * (unsigned)(C * 4);
 
     // ---- running shared-memory addresses
-    unsigned gr = geo_w + q * 16;                                          // read: + t*GEO_PLANE + v*PPW*16
+    unsigned gr = geo_w + q * (kRec ? 64 : 16);                            // read: + t*GEO_PLANE (+ v*PPW*16 | + field*16)
     // write (other buffer): chain 0's entry; chain k (same view, LPP = 4) is 2*k planes further
     static_assert(NVL == 1, "one view per lane: LPP = 8 or 4");
-    unsigned gw = geo_w + GEO_BUF + q * 16 + 2 * ((LPP == 8) ? (cg >> 2) : 0) * GEO_PLANE + jview[0] * PPW * 16;
+    unsigned gw = geo_w + GEO_BUF + 2 * ((LPP == 8) ? (cg >> 2) : 0) * GEO_PLANE +
+                  (kRec ? q * 64 + jview[0] * 4 : q * 16 + jview[0] * PPW * 16);
     unsigned gflip = GEO_BUF;                                              // +/- distance between the buffers
     // output rows of this lane: variance / weighted product / groups of 1 channel: its 4 channels; groups of 2:
     // two rows; wider groups: one row, written by the first lane of the group.  Row r of a staged plane is
@@ -351,8 +356,14 @@ sweep_quad_kernel(const SweepParams p) {
     auto store_chain = [&](int k, const float4& ea, const float4& eb, unsigned base) {
         if (owner[0]) {
             const unsigned a = base + (LPP == 8 ? 0 : 2 * k) * GEO_PLANE;
-            sts128(a, ea);
-            sts128(a + GEO_PLANE, eb);
+            if constexpr (kRec) {                    // this view's word of the four fields of the pixel's record
+                sts32(a, ea.w); sts32(a + 16, ea.x); sts32(a + 32, ea.y); sts32(a + 48, ea.z);
+                sts32(a + GEO_PLANE, eb.w); sts32(a + GEO_PLANE + 16, eb.x); sts32(a + GEO_PLANE + 32, eb.y);
+                sts32(a + GEO_PLANE + 48, eb.z);
+            } else {
+                sts128(a, ea);
+                sts128(a + GEO_PLANE, eb);
+            }
         }
     };
     auto project_chain = [&](int k, const float2 (&d)[2], float4& ea, float4& eb) {
@@ -411,8 +422,16 @@ sweep_quad_kernel(const SweepParams p) {
 
     float4 g[NV];
     auto load_table = [&](unsigned base) {
+        if constexpr (kRec) {
+            const float4 K = lds128(base), FX = lds128(base + 16), FY = lds128(base + 32), FXY = lds128(base + 48);
+            const float kk[4] = {K.x, K.y, K.z, K.w}, fx[4] = {FX.x, FX.y, FX.z, FX.w}, fy[4] = {FY.x, FY.y, FY.z, FY.w},
+                        fxy[4] = {FXY.x, FXY.y, FXY.z, FXY.w};
 #pragma unroll
-        for (int v = 0; v < NV; ++v) g[v] = lds128(base + v * PPW * 16);
+            for (int v = 0; v < NV; ++v) g[v] = make_float4(fx[v], fy[v], fxy[v], kk[v]);     // register renaming only
+        } else {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) g[v] = lds128(base + v * PPW * 16);
+        }
     };
     __syncwarp();                                    // table buffer 0 is complete
     load_table(gr);
@@ -448,12 +467,23 @@ sweep_quad_kernel(const SweepParams p) {
             float pm[4] = {0.f, 0.f, 0.f, 0.f};      // pair mean: this lane's partial dot product per view
             float dsum = 0.f;                        // kDot, group-wise: sum over the views
             if constexpr (kDot) {
+                // PA + fx*PB + fy*PC + fxy*PD per view, two views per packed operation (the record layout hands fx, fy, fxy
+                // of views (0,1) and (2,3) over in adjacent registers)
 #pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    const float o = fmaf(g[v].z, dotc[v][3], fmaf(g[v].y, dotc[v][2], fmaf(g[v].x, dotc[v][1], dotc[v][0])));
-                    pm[v] = o;
-                    dsum = v == 0 ? o : dsum + o;
+                for (int v = 0; v + 1 < NV; v += 2) {
+                    float2 o = __ffma2_rn(f2(g[v].x, g[v + 1].x), f2(dotc[v][1], dotc[v + 1][1]), f2(dotc[v][0], dotc[v + 1][0]));
+                    o = __ffma2_rn(f2(g[v].y, g[v + 1].y), f2(dotc[v][2], dotc[v + 1][2]), o);
+                    o = __ffma2_rn(f2(g[v].z, g[v + 1].z), f2(dotc[v][3], dotc[v + 1][3]), o);
+                    pm[v] = o.x;
+                    pm[v + 1] = o.y;
                 }
+                if (NV & 1) {
+                    constexpr int v = NV - 1;
+                    pm[v] = fmaf(g[v].z, dotc[v][3], fmaf(g[v].y, dotc[v][2], fmaf(g[v].x, dotc[v][1], dotc[v][0])));
+                }
+                dsum = pm[0];
+#pragma unroll
+                for (int v = 1; v < NV; ++v) dsum += pm[v];
             }
 #pragma unroll
             for (int v = 0; v < (kDot ? 0 : NV); ++v) {
@@ -563,7 +593,7 @@ sweep_quad_kernel(const SweepParams p) {
 
 template <int NV, int MODE, int LPP>
 int launch_sweep_quad(const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div) {
-    const size_t smem = 64 + (size_t)8 * 2 * kQuadPlanes * (NV <= 2 ? 2 : 4) * (32 / LPP) * 16 +
+    const size_t smem = 64 + (size_t)8 * 2 * kQuadPlanes * ((LPP == 8 || NV > 2) ? 4 : 2) * (32 / LPP) * 16 +
                         (size_t)kQuadBuffers * kQuadPlanes * 32 * 32 * 4 +
                         (p.perpix ? 0 : (size_t)(p.d_chunk + kLeanHypPad) * 4);
     if (smem > 110 * 1024) return -1;                // keep two CTAs per SM; absurd depth chunks go elsewhere
