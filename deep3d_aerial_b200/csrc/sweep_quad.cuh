@@ -249,6 +249,10 @@ sweep_quad_kernel(const SweepParams p) {
                                                        : (unsigned)((PPW * (row0 >> rpl_log2)) & 31);
     unsigned tw = tile_g + (row0 * PIX + ((warp * PPW + q) ^ swz_w)) * 4;  // + k*PIX*4 per row
     unsigned dr;                                           // drain: staged row chunk this lane moves
+    // plane stride of the volume in bytes, opaque to the compiler: written as `optr += p.out_sd` the advance is re-derived
+    // from the uniform register every plane (two moves, LEA, LEA.HI.X and another move: 5 instructions; now IADD3 + IADD3.X)
+    unsigned long long sd_bytes;
+    asm volatile("shl.b64 %0, %1, 2;" : "=l"(sd_bytes) : "l"(p.out_sd));
     float* optr;                                           // drain: where it goes
     bool drain_row;                                        // fewer than 32 rows (group-wise correlation)
     {
@@ -396,7 +400,7 @@ sweep_quad_kernel(const SweepParams p) {
                          "f"(w.z), "f"(w.w) : "memory");
         }
         dr += TILE_PLANE;
-        optr += p.out_sd;
+        optr = reinterpret_cast<float*>(reinterpret_cast<unsigned long long>(optr) + sd_bytes);
     };
     // Long sweeps (one-block re-fetch) read the staged chunk at the top of a plane and store it at the bottom, so the
     // store never waits on shared memory (cfg2: 5.555 -> 5.49 ms); the short-sweep flavour has no registers to
@@ -412,7 +416,7 @@ sweep_quad_kernel(const SweepParams p) {
         if ((MODE != D3D_AGG_GROUP_CORR && MODE != D3D_AGG_PAIR_MEAN) || drain_row)
             asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(optr), "f"(dw.x), "f"(dw.y),
                          "f"(dw.z), "f"(dw.w) : "memory");
-        optr += p.out_sd;
+        optr = reinterpret_cast<float*>(reinterpret_cast<unsigned long long>(optr) + sd_bytes);
     };
     auto begin_drain = [&]() {
         mbar_wait(bar_d, par_d);
