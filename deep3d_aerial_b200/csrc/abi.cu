@@ -44,6 +44,8 @@ int sweep_quad_weighted_product(int nv, const SweepParams& p, dim3 grid, cudaStr
 int sweep_quad_pair_mean(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div);
 int sweep_direct_variance(int nv, const SweepParams& p, cudaStream_t stream);
 int sweep_direct_weighted_product(int nv, const SweepParams& p, cudaStream_t stream);
+int sweep_acc_weighted_product(int nv, const SweepParams& p, cudaStream_t stream, bool ieee_div);
+int sweep_win_weighted_product(int nv, const SweepParams& p, cudaStream_t stream, bool ieee_div);
 
 static int sm_count() {
     static int cached = 0;
@@ -154,11 +156,34 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
     // variant 0: production kernels (sweep_quad for 32- / 16-channel features, sweep_direct for 8, sweep_lean / sweep_base for
     //            what those are not instantiated for);  1: baseline kernel (sweep_base) everywhere;  2: variant 0 with
     //            __fdiv_rn instead of the shared-reciprocal division;  6: sweep_lean where variant 0 picks sweep_quad;
-    //            7: sweep_quad spelled out;  8 / 9: the TMA-prefetch experiments (sweep_ws / sweep_pre);  >= 16: A/B flag
+    //            7: sweep_quad spelled out;  8 / 9: the TMA-prefetch experiments (sweep_ws / sweep_pre);  10 - 14: sweep_acc / sweep_win
+    //            A/B (below);  >= 16: A/B flag
     //            bits of the production kernel (variant - 16 -> SweepParams.flags).
     // Shapes a kernel is not instantiated for fall through to the next one.
     int variant = a->variant;
     if (variant >= 16) { p.flags = variant - 16; variant = 0; }   // A/B switches of the production kernel
+    // view-weighted product volume of the short per-pixel-hypothesis stages (cascade stages 2 and 3: 16 / 8 channels):
+    // planes accumulated in registers, one footprint alive per lane, gathered from a TMA-fetched shared-memory window of
+    // the source view (sweep_win.cuh) or straight from global memory (sweep_acc.cuh).  variant 12 / 13: sweep_win with
+    // 8 / 4 planes per lane;  10 / 14: sweep_acc (4 planes per lane / its alternative configuration);  11: the kernels
+    // that served these shapes before (sweep_direct, sweep_quad).
+    if (a->mode == D3D_AGG_WEIGHTED_PRODUCT && (C == 8 || C == 16 || C == 32) && variant != 1 && variant != 11) {
+        int rc = -1;
+        const bool ieee = variant == 2;
+        const int flags = p.flags;
+        if ((variant == 12 || variant == 13) && C != 32) {
+            p.flags = variant == 13;
+            rc = sweep_win_weighted_product(nv, p, stream, false);
+        } else if (variant == 10 || variant == 14) {
+            p.flags = variant == 14;
+            rc = sweep_acc_weighted_product(nv, p, stream, false);
+        } else if ((variant == 0 || variant == 2) && C == 8) {
+            rc = sweep_acc_weighted_product(nv, p, stream, ieee);
+        }
+        p.flags = flags;
+        if (rc >= 0) return rc;
+    }
+    if (variant >= 10 && variant <= 14) variant = 0;
     // 8-channel features (cascade stage 3): direct gather, one lane per pixel (sweep_direct.cuh)
     if (variant == 0 && C == 8 && nv <= 4 && (a->mode == D3D_AGG_VARIANCE || a->mode == D3D_AGG_WEIGHTED_PRODUCT)) {
         const int rc = a->mode == D3D_AGG_VARIANCE ? sweep_direct_variance(nv, p, stream)

@@ -27,15 +27,6 @@ __device__ __forceinline__ float2 lds64(unsigned addr) {
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ float2 fadd2_rd(float2 a, float2 b) {       // packed round-down add (FADD2.RM)
-    float2 r;
-    asm("add.rm.f32x2 %0, %1, %2;"
-        : "=l"(*reinterpret_cast<unsigned long long*>(&r))
-        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-    return r;
-}
-__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
-
 constexpr bool kQuadThreeCtas = true;   // <= 2 source views: 32 footprint registers, three CTAs per SM
 constexpr int kQuadPlanes = 4;       // planes per pass = planes per staged batch
 constexpr int kQuadBuffers = 4;      // staging ring: batches

@@ -392,17 +392,44 @@ def test_group_corr_wide_groups_lane_reduction():
     assert rel_norm_err(got, want) < VOL_TOL
 
 
-@pytest.mark.parametrize("c,h,w", [(16, 36, 44), (32, 40, 48), (16, 32, 64), (8, 64, 64)])   # base / quad kernels
+@pytest.mark.parametrize("c,h,w", [(16, 36, 44), (32, 40, 48), (16, 32, 64), (8, 64, 64)])   # base / quad / acc kernels
 @pytest.mark.parametrize("eps_num", [False, True])
-def test_weighted_product_matches_oracle(eps_num, c, h, w):
+@pytest.mark.parametrize("variant", [0, 10, 11, 12, 13, 14])   # production; sweep_acc / sweep_win A/B forms (abi.cu)
+def test_weighted_product_matches_oracle(eps_num, c, h, w, variant):
     v, d = 5, 8
     _, proj, feats, hyps = _scene(v, c, d, h, w, seed=7, perpixel=True)
     g = torch.Generator().manual_seed(1)
     weights = [torch.rand(1, 1, h // 2, w // 2, generator=g) for _ in range(v - 1)]
     want = sweep_torch.weighted_product_volume(_views(feats), proj, hyps, weights, eps_in_numerator=eps_num)[0]
     wt = torch.cat([sweep_torch.resize_weight(x, h, w) for x in weights], 1)[0].to(DEV).contiguous()
-    got = _ours_volume(feats, proj, hyps, sweep.AGG_WEIGHTED_PRODUCT, weights=wt, eps_in_numerator=eps_num)
+    got = _ours_volume(feats, proj, hyps, sweep.AGG_WEIGHTED_PRODUCT, weights=wt, eps_in_numerator=eps_num, variant=variant)
     assert rel_norm_err(got, want) < VOL_TOL
+
+
+@pytest.mark.parametrize("v,c,d,h,w,perpixel", [(5, 8, 8, 45, 67, True), (3, 8, 11, 33, 50, True), (4, 16, 32, 40, 56, True),
+                                                (5, 16, 19, 31, 37, False), (2, 32, 13, 24, 40, True), (5, 8, 3, 130, 3, False)])
+@pytest.mark.parametrize("variant", [10, 12, 13, 14])
+def test_register_accumulated_sweep_chunks_slices_and_borders(v, c, d, h, w, perpixel, variant):
+    """sweep_acc.cuh / sweep_win.cuh (variants 10, 14 / 12, 13 force them wherever they are instantiated): chunks of 4 or 8 planes with a ragged last
+    chunk, ragged pixel tiles, uniform and per-pixel hypotheses, 1..4 source views; every plane-slice launch and the
+    plane-major layout reproduce the whole-volume launch bit for bit (a plane's result does not depend on which
+    footprint the lane happened to hold); the synthetic rig's oblique views put part of every source image out of
+    bounds, so the zeros-padding side path runs."""
+    _, proj, feats, hyps = _scene(v, c, d, h, w, seed=70 + c + d, perpixel=perpixel)
+    g = torch.Generator().manual_seed(d)
+    weights = [torch.rand(1, 1, h, w, generator=g) for _ in range(v - 1)]
+    want = sweep_torch.weighted_product_volume(_views(feats), proj, hyps, weights)[0]
+    wt = torch.cat(weights, 1)[0].to(DEV).contiguous()
+    kw = dict(weights=wt, variant=variant)
+    full = _ours_volume(feats, proj, hyps, sweep.AGG_WEIGHTED_PRODUCT, **kw)
+    assert rel_norm_err(full, want) < VOL_TOL
+    pm = _ours_volume(feats, proj, hyps, sweep.AGG_WEIGHTED_PRODUCT, plane_major=True, **kw)
+    assert torch.equal(pm.permute(1, 0, 2, 3), full)
+    for d0, dn in ((0, 1), (d // 2, 2), (1, d - 1), (max(d - 9, 0), min(9, d))):
+        part = _ours_volume(feats, proj, hyps, sweep.AGG_WEIGHTED_PRODUCT, d_begin=d0, d_count=dn, **kw)
+        assert torch.equal(part, full[:, d0:d0 + dn])
+    old = _ours_volume(feats, proj, hyps, sweep.AGG_WEIGHTED_PRODUCT, weights=wt, variant=11)
+    assert rel_norm_err(full, old) < 1e-5      # the kernels it replaces (differenced corners instead of corner weights)
 
 
 @pytest.mark.parametrize("v,h,w", [(5, 43, 29), (5, 40, 48), (3, 32, 40)])      # base kernel / quad kernel

@@ -38,5 +38,6 @@ for v in [0] + [x for x in variants if x != 0]:
     torch.cuda.synchronize()
     if base is None:
         base = out.clone()
-    print("stage %d (C=%d D=%d %dx%d) variant %2d: %.3f ms  identical to variant 0: %s"
-          % (stage, c, d, h, w, v, a.elapsed_time(b) / 10, bool(torch.equal(out, base))))
+    err = float((out - base).norm() / base.norm())
+    print("stage %d (C=%d D=%d %dx%d) variant %2d: %.3f ms  identical to variant 0: %s (rel diff %.2e)"
+          % (stage, c, d, h, w, v, a.elapsed_time(b) / 10, bool(torch.equal(out, base)), err))
