@@ -416,9 +416,15 @@ sweep_quad_kernel(const SweepParams p) {
     };
 
     float4 g[NV];
+    // record layout, long sweeps: the keys of the NEXT plane are read right after this plane's move test (they are all that
+    // test needs, and nothing between the two tests writes them), the fractions after the arithmetic as before: the test at
+    // the top of a plane no longer waits on the table read (short-scoreboard stalls were 7 % of the samples)
+    constexpr bool kEarlyKeys = kRec && !kSplit && !kDot && MODE == D3D_AGG_VARIANCE;
+    float4 knext;
     auto load_table = [&](unsigned base) {
         if constexpr (kRec) {
-            const float4 K = lds128(base), FX = lds128(base + 16), FY = lds128(base + 32), FXY = lds128(base + 48);
+            const float4 K = kEarlyKeys ? knext : lds128(base);
+            const float4 FX = lds128(base + 16), FY = lds128(base + 32), FXY = lds128(base + 48);
             const float kk[4] = {K.x, K.y, K.z, K.w}, fx[4] = {FX.x, FX.y, FX.z, FX.w}, fy[4] = {FY.x, FY.y, FY.z, FY.w},
                         fxy[4] = {FXY.x, FXY.y, FXY.z, FXY.w};
 #pragma unroll
@@ -429,6 +435,7 @@ sweep_quad_kernel(const SweepParams p) {
         }
     };
     __syncwarp();                                    // table buffer 0 is complete
+    if (kEarlyKeys) knext = lds128(gr);
     load_table(gr);
 
     int n = 0;
@@ -453,6 +460,14 @@ sweep_quad_kernel(const SweepParams p) {
                     RefetchTok<NV, C * 4>::run_shift(tex, ckey, g, feats_c, row_bytes, p.HW, p.W, p.H, rf);
                 } else {
                     RefetchTok<NV, C * 4>::run(tex, ckey, g, feats_c, row_bytes, p.HW, p.W, p.H);
+                }
+            }
+            if constexpr (kEarlyKeys) {
+                if (t + 1 < KT) {
+                    knext = lds128(gr + (t + 1) * GEO_PLANE);
+                } else {                             // last plane of the pass: the other table (complete since plane JPL - 1)
+                    __syncwarp();
+                    knext = lds128(gr + gflip);
                 }
             }
             float4 ea, eb;
@@ -515,7 +530,7 @@ sweep_quad_kernel(const SweepParams p) {
             if (t + 1 < KT) {
                 load_table(gr + (t + 1) * GEO_PLANE);
             } else {                                 // last plane of the pass: swap the table buffers
-                __syncwarp();                        // the other table is complete; this one is free
+                if (!kEarlyKeys) __syncwarp();       // the other table is complete; this one is free
                 gr += gflip;
                 gw -= gflip;
                 gflip = 0u - gflip;
