@@ -399,9 +399,8 @@ sweep_quad_kernel(const SweepParams p) {
     // (cfg4: 5.15 -> 5.26 ms with it): both keep the back-to-back form.
     constexpr bool kEarlyDrain = !kSplit && MODE == D3D_AGG_VARIANCE;
     float4 dw;                                       // the staged chunk this plane's iteration writes out
-    auto drain_load = [&]() {                        // top of a plane: the LDS has the whole plane to land
-        dw = lds128(dr);
-        dr += TILE_PLANE;
+    auto drain_load = [&](int t) {                   // top of a plane: the LDS has the whole plane to land
+        dw = lds128(dr + t * TILE_PLANE);            // (an immediate offset; `dr` advances once per batch)
     };
     auto drain_store = [&]() {                       // bottom of the plane
         if ((MODE != D3D_AGG_GROUP_CORR && MODE != D3D_AGG_PAIR_MEAN) || drain_row)
@@ -445,7 +444,7 @@ sweep_quad_kernel(const SweepParams p) {
         if (draining) begin_drain();
 #pragma unroll
         for (int t = 0; t < KT; ++t) {
-            if (kEarlyDrain && draining) drain_load();
+            if (kEarlyDrain && draining) drain_load(t);
             unsigned moved = 0;
 #pragma unroll
             for (int v = 0; v < NV; ++v) moved |= __float_as_uint(g[v].w) ^ ckey[v];
@@ -591,6 +590,7 @@ sweep_quad_kernel(const SweepParams p) {
         bar_c += 8;
         tw += TILE_BUF;
         if (++slot_c == NBUF) { slot_c = 0; bar_c = bar0; tw -= TILE_RING; }
+        if (kEarlyDrain && draining) dr += KT * TILE_PLANE;
         if (draining && slot_d == 0) dr -= TILE_RING;   // the drained slot was the last of the ring
     }
     // the sweep is over: the last two batches have nothing left to hide behind
