@@ -637,16 +637,24 @@ def run_cascade(args):
         ring = [[torch.empty((v + 1, s["c"], s["h"], s["w"]), device=dev) for s in stages]]
         for k, s in enumerate(stages):
             ring[0][k][:v].copy_(s["feats"])
-        out_host = torch.empty((2, full_h, full_w), dtype=torch.float32).pin_memory()
-        copy_stream = torch.cuda.Stream()
+        out_host = [torch.empty((2, full_h, full_w), dtype=torch.float32).pin_memory() for _ in range(2)]
+        copy_stream, down_stream = torch.cuda.Stream(), torch.cuda.Stream()
         arrived, consumed = torch.cuda.Event(), torch.cuda.Event()
+        computed, landed = torch.cuda.Event(), [torch.cuda.Event(), torch.cuda.Event()]
         consumed.record()
         h2d = sum(t.numel() * 4 for t in pyramid)
         sink = 0.0
 
-        def view(i):
-            """Views i uses ring slots i .. i+V-1 (mod V+1); the image of slot i+V (the next view's new one) is uploaded now."""
+        def collect(i):
+            """The host's read of view i's maps (its device->host copy was queued a view ago)."""
             nonlocal sink
+            landed[i & 1].synchronize()
+            sink += float(out_host[i & 1][0, 0, 0]) + float(out_host[i & 1][1, 0, 0])
+
+        def view(i):
+            """View i uses ring slots i .. i+V-1 (mod V+1); the image of slot i+V (the next view's new one) is uploaded now,
+            under this view's sweeps; its maps go device->host on a third stream under the NEXT view's sweeps, and the
+            host reads view i-1's maps meanwhile: nothing in the loop waits for the view it has just queued."""
             slot = (i + v) % (v + 1)
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed)                   # the view that last read this slot is done with it
@@ -658,26 +666,34 @@ def run_cascade(args):
                 s["feats"] = ring[0][k][order]                     # (gathers the V maps: stands in for FeatureNet's outputs)
             dep, conf = step()
             consumed.record()
+            computed.record()
             torch.cuda.current_stream().wait_event(arrived)        # the next view needs the image that just arrived
-            out_host[0].copy_(dep, non_blocking=True)
-            out_host[1].copy_(conf, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            sink += float(out_host[0, 0, 0]) + float(out_host[1, 0, 0])
+            with torch.cuda.stream(down_stream):
+                down_stream.wait_event(computed)
+                out_host[i & 1][0].copy_(dep, non_blocking=True)
+                out_host[i & 1][1].copy_(conf, non_blocking=True)
+                landed[i & 1].record()
+            dep.record_stream(down_stream)
+            conf.record_stream(down_stream)
+            if i > 0:
+                collect(i - 1)
 
         view(0)
+        collect(0)
         shard.barrier()
         torch.cuda.synchronize()
         t_host = time.perf_counter()
         for i in range(1, 1 + n_e2e):
             view(i)
+        collect(n_e2e)
         torch.cuda.synchronize()
         dt = shard.join_max(time.perf_counter() - t_host)
         if not math.isfinite(sink):
             raise SystemExit("bench.py: the cascade produced non-finite maps")
         e2e = {"value": shard.join_sum(vox * n_e2e) / dt / 1e9, "unit": "Gvoxel/s", "ms_per_step": dt / n_e2e * 1e3,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host.numel() * 4, "steps": n_e2e,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host[0].numel() * 4, "steps": n_e2e,
                "timer": "host wall clock", "stream": "one new image (feature pyramid of 3 maps) per reference view, "
-               "uploaded under the previous view's sweeps into a ring of V + 1 resident images"}
+               "uploaded under the view's sweeps into a ring of V + 1 resident images; the maps of view i come back under view i+1"}
     if rank != 0:
         return None
     cpu = None
