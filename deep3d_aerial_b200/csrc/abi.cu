@@ -153,7 +153,8 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
     };
     dim3 grid;
 
-    // variant 0: production kernels (sweep_quad for 32- / 16-channel features, sweep_direct for 8, sweep_lean / sweep_base for
+    // variant 0: production kernels (sweep_quad for 32- / 16-channel features; 8 channels: sweep_acc for the weighted product,
+    //            sweep_direct for the variance; sweep_lean / sweep_base for
     //            what those are not instantiated for);  1: baseline kernel (sweep_base) everywhere;  2: variant 0 with
     //            __fdiv_rn instead of the shared-reciprocal division;  6: sweep_lean where variant 0 picks sweep_quad;
     //            7: sweep_quad spelled out;  8 / 9: the TMA-prefetch experiments (sweep_ws / sweep_pre);  10 - 14: sweep_acc / sweep_win
