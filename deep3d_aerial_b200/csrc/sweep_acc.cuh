@@ -21,7 +21,9 @@
 //   (stage-3 shape on B200: 1.04 ms smooth depth map / 1.42 ms white-noise depth map, against 1.16 / 1.58 ms for
 //   sweep_direct; KP = 8: 1.09 ms).  Measured and not adopted: `prefetch.global.L1` of the next pair's footprints
 //   (projection run one pair ahead, across the view boundary too): 1.17 ms; 16 channels per lane for the stage-2 shape:
-//   2.5-3.1 ms against sweep_quad's 1.8 ms (216 registers, or spills at 168); two lanes per pixel there: 2.6 ms.
+//   2.5-3.1 ms against sweep_quad's 1.8 ms (216 registers, or spills at 168); two lanes per pixel there: 2.6 ms; the
+//   VARIANCE volume of an 8-channel stage in this form (sum and sum of squares double the accumulators: 4 planes per
+//   lane at 12 warps per SM, or 2 planes at 20): 1.40 / 1.33 ms against sweep_direct's 1.15 ms -- not instantiated.
 //   sweep_win.cuh is this kernel with the footprints read from a TMA-fetched shared-memory window.
 #pragma once
 #include <type_traits>

@@ -7,6 +7,10 @@ import torch
 sys.path.insert(0, ".")
 from deep3d_aerial_b200 import sweep, synth  # noqa: E402
 
+mode = sweep.AGG_WEIGHTED_PRODUCT
+if sys.argv[1] == "variance":                  # python tools/stage_ab.py variance <stage> <variant> ...
+    mode = sweep.AGG_VARIANCE
+    del sys.argv[1]
 stage = int(sys.argv[1])
 variants = [int(v) for v in sys.argv[2:]] or [0]
 scale, c, d, ratio = {1: (4, 32, 48, 4.0), 2: (2, 16, 32, 2.0), 3: (1, 8, 8, 1.0)}[stage]
@@ -26,14 +30,14 @@ weights = torch.rand(4, h, w, generator=g).to(dev)
 rays = sweep.rays_for(pose, h, w)
 base = None
 for v in [0] + [x for x in variants if x != 0]:
-    out = sweep.cost_volume(tex, pose, hyps, sweep.AGG_WEIGHTED_PRODUCT, weights=weights, plane_major=True, rays=rays, variant=v)
+    out = sweep.cost_volume(tex, pose, hyps, mode, weights=(weights if mode == sweep.AGG_WEIGHTED_PRODUCT else None), plane_major=True, rays=rays, variant=v)
     for _ in range(3):
-        sweep.cost_volume(tex, pose, hyps, sweep.AGG_WEIGHTED_PRODUCT, weights=weights, plane_major=True, rays=rays, variant=v, out=out)
+        sweep.cost_volume(tex, pose, hyps, mode, weights=(weights if mode == sweep.AGG_WEIGHTED_PRODUCT else None), plane_major=True, rays=rays, variant=v, out=out)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     a.record()
     for _ in range(10):
-        sweep.cost_volume(tex, pose, hyps, sweep.AGG_WEIGHTED_PRODUCT, weights=weights, plane_major=True, rays=rays, variant=v, out=out)
+        sweep.cost_volume(tex, pose, hyps, mode, weights=(weights if mode == sweep.AGG_WEIGHTED_PRODUCT else None), plane_major=True, rays=rays, variant=v, out=out)
     b.record()
     torch.cuda.synchronize()
     if base is None:
