@@ -11,6 +11,8 @@
 // msrednet.py:418-437 (streaming un-normalised exp), module.py:605-613 (depth_regression incl. the
 // bilinear resize of 4-D hypotheses), ucsnet.py:148-149 (exp_variance), module.py:616-630
 // (next-stage samples).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace d3d {
@@ -365,20 +367,38 @@ __global__ void __launch_bounds__(256) regress_rawexp_kernel(const RegressParams
     // way the compiler interleaved loads and the tap arithmetic, and the kernel sat on the long scoreboard for 11
     // cycles per issued instruction, profiles/ncu_r1_cfg3.txt).
     constexpr int G = (HYPS == D3D_HYPS_RESIZED) ? 4 : kGroup;
+    const size_t hplane = (size_t)p.hh * p.hw;
+    const float* row0 = p.hyps + (size_t)p.d_begin * hplane + tap.o00;       // resized hypotheses: north-west / south-west tap
+    const float* row1 = p.hyps + (size_t)p.d_begin * hplane + tap.o10;
+    const int xstep = tap.o01 - tap.o00;                                     // 1, or 0 in the last column
+    const bool step1 = __all_sync(__activemask(), xstep == 1);
     for (int k0 = 0; k0 < p.d_count; k0 += G) {
         float x[G], d[G];
         if (HYPS == D3D_HYPS_RESIZED) {
+            // Round 2: with the loads batched the kernel was ISSUE-bound (79 % issue utilisation at 36 % of the HBM rate, 76
+            // instructions per plane and warp, a third of them address arithmetic).  The four taps of a plane sit at fixed
+            // offsets from its north-west tap: two row pointers run from plane to plane, and when every lane of the warp
+            // has a right-hand neighbour (everywhere but the last column) the east taps are an immediate +1 -- 4 address
+            // instructions per plane where forming each tap's address from the plane index took 20.
             float t00[G], t01[G], t10[G], t11[G];
+            auto load_taps = [&](auto step_c) {
+                constexpr bool kStep1 = decltype(step_c)::value;
 #pragma unroll
-            for (int j = 0; j < G; ++j) {
-                const int k = k0 + j;
-                const bool ok = k < p.d_count;
-                const float* src = p.logits ? lg + (size_t)k * p.stride_d : p.planes[ok ? k : 0] + pix;
-                const float* q = p.hyps + (size_t)(p.d_begin + (ok ? k : 0)) * p.hh * p.hw;
-                x[j] = ok ? __ldg(src) : -INFINITY;
-                t00[j] = __ldg(q + tap.o00); t01[j] = __ldg(q + tap.o01);
-                t10[j] = __ldg(q + tap.o10); t11[j] = __ldg(q + tap.o11);
-            }
+                for (int j = 0; j < G; ++j) {
+                    const int k = k0 + j;
+                    const bool ok = k < p.d_count;
+                    const float* src = p.logits ? lg + (size_t)k * p.stride_d : p.planes[ok ? k : 0] + pix;
+                    x[j] = ok ? __ldg(src) : -INFINITY;
+                    t00[j] = t01[j] = t10[j] = t11[j] = 0.f;
+                    if (ok) {                              // (planes past the slice are not dereferenced)
+                        t00[j] = __ldg(row0); t01[j] = __ldg(row0 + (kStep1 ? 1 : xstep));
+                        t10[j] = __ldg(row1); t11[j] = __ldg(row1 + (kStep1 ? 1 : xstep));
+                    }
+                    row0 += hplane;
+                    row1 += hplane;
+                }
+            };
+            if (step1) load_taps(std::true_type()); else load_taps(std::false_type());
 #pragma unroll
             for (int j = 0; j < G; ++j)                  // the expression of hyp_at<RESIZED>
                 d[j] = tap.h0 * (tap.w0 * t00[j] + tap.w1 * t01[j]) + tap.h1 * (tap.w0 * t10[j] + tap.w1 * t11[j]);
