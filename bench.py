@@ -571,7 +571,7 @@ def run_cascade(args):
             else:
                 hyps = sweep.depth_samples(sweep.SAMPLES_AROUND, s["d"], (s["h"], s["w"]), cur=depth,
                                            interval=s["ratio"] * base_interval)
-                conf = F.interpolate(conf.unsqueeze(0), [s["h"], s["w"]], mode="bilinear", align_corners=False)[0]
+                conf = sweep.resize_bilinear(conf, (s["h"], s["w"]))       # adamvs.py:498-503, one launch for the V-1 maps
             mark("s%d_sweep" % (i + 1))
             sim = sweep.cost_volume(tex, s["pose"], hyps, sweep.AGG_WEIGHTED_PRODUCT, weights=conf.contiguous(),
                                     plane_major=True, rays=rays)

@@ -85,6 +85,7 @@ EXPORTS = {
     "d3d_depth_samples": (C.c_int, [C.POINTER(SamplesArgs), C.c_void_p]),
     "d3d_consistency_fuse": (C.c_int, [C.POINTER(FuseArgs), C.c_void_p]),
     "d3d_pixel_rays": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "d3d_resize_bilinear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "d3d_homo_warp_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_void_p, C.c_void_p]),
     "d3d_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

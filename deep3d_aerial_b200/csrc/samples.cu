@@ -291,6 +291,41 @@ extern "C" int d3d_pixel_rays(const float* pose, int32_t num_src, int32_t height
     return check_launch("pixel_rays_kernel");
 }
 
+// F.interpolate(x, [H, W], mode="bilinear", align_corners=False) for a stack of maps (the AdaMVS pair confidences between
+// stages, adamvs.py:291-302): ATen's upsample_bilinear2d formula -- src = scale * (dst + 0.5) - 0.5 clamped at 0, i1 =
+// (int)src, lambda1 = src - i1, out = h0 * (w0 * t00 + w1 * t01) + h1 * (w0 * t10 + w1 * t11) -- one thread per output
+// pixel, every map of the stack from the same taps.
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int hi,
+                                                              int wi, int ho, int wo, float sh, float sw) {
+    const int pix = blockIdx.x * 256 + threadIdx.x;
+    if (pix >= ho * wo) return;
+    const int y = pix / wo, x = pix - y * wo;
+    const float sy = fmaxf(sh * ((float)y + 0.5f) - 0.5f, 0.f), sx = fmaxf(sw * ((float)x + 0.5f) - 0.5f, 0.f);
+    const int y1 = (int)sy, x1 = (int)sx;
+    const int yp = (y1 < hi - 1) ? 1 : 0, xp = (x1 < wi - 1) ? 1 : 0;
+    const float h1 = sy - (float)y1, h0 = 1.f - h1, w1 = sx - (float)x1, w0 = 1.f - w1;
+    const float* a = src + (size_t)y1 * wi + x1;
+    const float* b = a + (size_t)yp * wi;
+    const size_t in_map = (size_t)hi * wi, out_map = (size_t)ho * wo;
+    for (int c = 0; c < n; ++c, a += in_map, b += in_map)
+        dst[(size_t)c * out_map + pix] = h0 * (w0 * __ldg(a) + w1 * __ldg(a + xp)) + h1 * (w0 * __ldg(b) + w1 * __ldg(b + xp));
+}
+
+extern "C" int d3d_resize_bilinear(const float* in, float* out, int32_t maps, int32_t in_height, int32_t in_width,
+                                   int32_t out_height, int32_t out_width, void* cuda_stream) {
+    if (!in || !out) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_resize_bilinear: NULL pointer");
+    if (maps < 1 || in_height < 1 || in_width < 1 || out_height < 1 || out_width < 1 ||
+        (long long)out_height * out_width > INT32_MAX || (long long)in_height * in_width > INT32_MAX)
+        return fail(D3D_ERR_BAD_ARGUMENT, "d3d_resize_bilinear: bad extent N=%d %dx%d -> %dx%d", maps, in_height, in_width,
+                    out_height, out_width);
+    const int hw = out_height * out_width;
+    resize_bilinear_kernel<<<(hw + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(
+        in, out, maps, in_height, in_width, out_height, out_width, (float)in_height / (float)out_height,
+        (float)in_width / (float)out_width);
+    count_launch();
+    return check_launch("resize_bilinear_kernel");
+}
+
 extern "C" int d3d_nchw_to_nhwc(const float* in, float* out, int32_t channels, int32_t height, int32_t width,
                                 void* cuda_stream) {
     if (!in || !out) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_nchw_to_nhwc: NULL pointer");

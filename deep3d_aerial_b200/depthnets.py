@@ -94,6 +94,21 @@ def _volume(features, proj_matrices, depth_values, mode, plane_major=False, scen
         return torch.stack(vols, 0) if len(vols) > 1 else vols[0].unsqueeze(0)
 
 
+def _resize_pair_weights(confidence_map, n_src, img_h, img_w):
+    """adamvs.py:291-302, :498-503: the first V-1 pair-confidence maps [B,1,h',w'] resized (bilinear, align_corners=False)
+    to the stage's resolution -> (list of V-1 maps [B,1,h,w], stacked weights [B,V-1,h,w]).  On the device the maps are
+    stacked at THEIR size and one launch (sweep.resize_bilinear: ATen's formula) writes the stacked weights; the list
+    holds views of them (upstream: V-1 upsample launches and a concatenation at the stage's full size)."""
+    maps = [confidence_map[i] for i in range(n_src)]
+    if (all(m.is_cuda and m.dtype == torch.float32 and m.dim() == 4 and m.shape[1] == 1 for m in maps)
+            and len({tuple(m.shape) for m in maps}) == 1):
+        stacked = torch.cat(maps, 1) if n_src > 1 else maps[0]
+        weights = stacked if tuple(stacked.shape[-2:]) == (img_h, img_w) else sweep.resize_bilinear(stacked, (img_h, img_w))
+        return [weights[:, i:i + 1] for i in range(n_src)], weights
+    resized = [F.interpolate(m, [img_h, img_w], mode='bilinear', align_corners=False) for m in maps]
+    return resized, torch.cat(resized, 1)
+
+
 def _regress(logits, depth_values, **kw):
     """depth_regress per batch item; logits [B,D,H,W]; returns dict of stacked [B,...] tensors."""
     outs = [sweep.depth_regress(logits[b], depth_values[b].contiguous(), **kw) for b in range(logits.shape[0])]
@@ -249,9 +264,7 @@ def ada_infer_forward(self, features, proj_matrices, depth_values, num_depth, co
 
     # :498-503 -- zip() stops at the V-1 source views, so only the first V-1 maps are consumed; every
     # depth iteration appends the resized maps again (kept: callers index the list)
-    resized = [F.interpolate(confidence_map[i], [img_h, img_w], mode='bilinear', align_corners=False)
-               for i in range(n_src)]
-    weights = torch.cat(resized, 1)                                                             # [B,V-1,h,w]
+    resized, weights = _resize_pair_weights(confidence_map, n_src, img_h, img_w)                # [B,V-1,h,w]
     if PLANE_LOOP_GRAPHS and depth_values.dim() == 4:
         loop = _plane_loop(self, "ada", self.reg_fuse, b_num, num_depth, ref.shape[1], (img_h, img_w),
                            (img_h * up, img_w * up), [tuple(state1.shape), tuple(state2.shape)],
@@ -304,10 +317,8 @@ def ada_depthnet_forward(self, features, proj_matrices, depth_values, num_depth,
             pair_confidence.append(r["conf"].unsqueeze(1))
         weights = torch.cat(pair_confidence, 1)
     else:
-        resized = [F.interpolate(confidence_map[i], [img_h, img_w], mode='bilinear', align_corners=False)
-                   for i in range(n_src)]
+        _, weights = _resize_pair_weights(confidence_map, n_src, img_h, img_w)
         pair_confidence = confidence_map            # adamvs.py:299: the caller's list, NOT the resized maps
-        weights = torch.cat(resized, 1)
     fused = _volume(features, proj_matrices, depth_values, sweep.AGG_WEIGHTED_PRODUCT, weights=weights,
                     eps_in_numerator=True, scenes=scenes)
     prob_volume_pre = self.reg_fuse(fused).squeeze(1)

@@ -56,6 +56,21 @@ def to_texels(features, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     return out
 
 
+def resize_bilinear(maps: torch.Tensor, hw: Tuple[int, int]) -> torch.Tensor:
+    """F.interpolate(maps, hw, mode="bilinear", align_corners=False) for [..., h, w] fp32 maps (ATen's formula, one launch
+    for the whole stack): the resize of the AdaMVS pair confidences between stages (adamvs.py:291-302)."""
+    maps = _need(maps, "maps")
+    h, w = int(hw[0]), int(hw[1])
+    if maps.dim() < 2:
+        raise ValueError("maps must be [..., h, w]")
+    n = maps.numel() // (maps.shape[-2] * maps.shape[-1])
+    out = torch.empty(tuple(maps.shape[:-2]) + (h, w), device=maps.device, dtype=torch.float32)
+    with torch.cuda.device(maps.device):
+        _lib.check(_lib.load().d3d_resize_bilinear(maps.data_ptr(), out.data_ptr(), n, maps.shape[-2], maps.shape[-1], h, w,
+                                                   _stream()))
+    return out
+
+
 def relative_poses(proj: torch.Tensor) -> torch.Tensor:
     """[V,4,4] projection matrices (view 0 = reference) -> [V-1,4,4] P_src @ inverse(P_ref).
 

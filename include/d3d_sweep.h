@@ -177,6 +177,11 @@ int d3d_depth_samples(const D3dSamplesArgs* args, void* cuda_stream);
  * it does, the sweeps form their rays themselves and the matmul (a 0.75 TB/s skinny GEMM) is skipped. */
 int d3d_pixel_rays(const float* pose, int32_t num_src, int32_t height, int32_t width, float* out, void* cuda_stream);
 
+/* out[N,Ho,Wo] = F.interpolate(in[N,Hi,Wi], [Ho,Wo], mode="bilinear", align_corners=False): the resize of the AdaMVS pair
+ * confidences between stages (mvs/mvs_cas/models/adamvs.py:291-302), ATen's upsample_bilinear2d formula. */
+int d3d_resize_bilinear(const float* in, float* out, int32_t maps, int32_t in_height, int32_t in_width,
+                        int32_t out_height, int32_t out_width, void* cuda_stream);
+
 /* ---- homo_warping_double: the warp with fp64 coordinate arithmetic (mvs/mvs_cas/models/module.py:560-601) -----
  * The reference forms rot @ [x,y,1], X = rot_xyz * d + trans, X/Z and u / ((W-1)/2) - 1 in fp64 (its projection
  * matrices must be fp64 for that: torch.matmul does not promote), casts the normalised grid to fp32 and samples it with

@@ -84,6 +84,8 @@ def test_validation_errors_need_no_gpu(lib):
     s.mode, s.num_depth, s.height, s.width = _lib.SAMPLES_AROUND, 1, 4, 4
     assert lib.d3d_depth_samples(C.byref(s), None) == _lib.ERR_BAD_ARGUMENT  # D < 2
     assert lib.d3d_nchw_to_nhwc(None, None, 4, 4, 4, None) == _lib.ERR_BAD_ARGUMENT
+    assert lib.d3d_resize_bilinear(None, None, 1, 4, 4, 8, 8, None) == _lib.ERR_BAD_ARGUMENT
+    assert lib.d3d_resize_bilinear(256, 256, 0, 4, 4, 8, 8, None) == _lib.ERR_BAD_ARGUMENT      # no maps
 
 
 def test_cpu_tensors_are_refused(lib):

@@ -859,3 +859,29 @@ def test_full_size_regression_against_cuda_aten():
     # shift invariance of the softmax: adding a constant to every logit changes nothing
     r2 = sweep.depth_regress(logits + 3.0, hyps)
     assert _depth_err(r2["depth"], r["depth"]) < 1e-5
+
+
+# ------------------------------------------------------- pair-confidence resize between AdaMVS stages (adamvs.py:291-302)
+@pytest.mark.parametrize("n,hi,wi,ho,wo", [(4, 58, 86, 116, 172), (4, 116, 172, 232, 344), (3, 17, 23, 40, 31), (2, 40, 31, 17, 23),
+                                          (1, 8, 8, 8, 8), (4, 1, 5, 3, 10)])
+def test_resize_bilinear_matches_aten(n, hi, wi, ho, wo):
+    g = torch.Generator().manual_seed(n * 1000 + hi)
+    maps = torch.rand(2, n, hi, wi, generator=g)
+    want = torch.nn.functional.interpolate(maps, [ho, wo], mode="bilinear", align_corners=False)       # CPU ATen
+    want_cuda = torch.nn.functional.interpolate(maps.to(DEV), [ho, wo], mode="bilinear", align_corners=False)
+    got = sweep.resize_bilinear(maps.to(DEV), (ho, wo))
+    assert got.shape == want.shape
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(got, want_cuda, rtol=1e-6, atol=1e-6)
+
+
+def test_resize_pair_weights_stacks_and_falls_through():
+    g = torch.Generator().manual_seed(5)
+    maps = [torch.rand(1, 1, 20, 30, generator=g).to(DEV) for _ in range(6)]         # an over-long list: V-1 = 4 are used
+    resized, weights = depthnets._resize_pair_weights(maps, 4, 40, 60)
+    want = [torch.nn.functional.interpolate(m, [40, 60], mode="bilinear", align_corners=False) for m in maps[:4]]
+    assert weights.shape == (1, 4, 40, 60) and len(resized) == 4
+    for r, w in zip(resized, want):
+        torch.testing.assert_close(r, w, rtol=1e-6, atol=1e-6)
+    same, wsame = depthnets._resize_pair_weights(maps, 4, 20, 30)                     # stage 1: same size, values untouched
+    assert all(torch.equal(a, b) for a, b in zip(same, maps[:4])) and torch.equal(wsame, torch.cat(maps[:4], 1))
