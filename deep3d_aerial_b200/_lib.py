@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libd3dsweep.so")
+# D3D_SWEEP_LIB: an A/B build of the same library (tools/build_ab.py); there is no other implementation to point it at
+LIB_PATH = os.environ.get("D3D_SWEEP_LIB") or os.path.join(HERE, "libd3dsweep.so")
 
 # enums (include/d3d_sweep.h)
 OK, ERR_BAD_ARGUMENT, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3

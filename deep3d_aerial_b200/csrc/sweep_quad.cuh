@@ -128,6 +128,9 @@ sweep_quad_kernel(const SweepParams p) {
     // four values of a kind land in adjacent registers with one LDS.128 (what packs the correlation modes' arithmetic over
     // view pairs).  Otherwise: one 16-byte entry {fx, fy, fx*fy, key} per (view, pixel).
     constexpr bool kRec = LPP == 8;
+    // fx * fy formed by the consumer instead of read from the record (see load_table): cfg4 3.34 -> 3.30 ms; the variance
+    // sweep, whose FP32 pipe is the busier unit, loses by it (cfg2 5.19 -> 5.23 ms)
+    constexpr bool kFxyLocal = kRec && kDot;
     constexpr int VS = kRec ? 4 : (NV <= 2 ? 2 : 4);       // view slots of the table
     constexpr unsigned GEO_PLANE = VS * PPW * 16;          // bytes: one plane's table of one warp
     constexpr unsigned GEO_BUF = KT * GEO_PLANE;
@@ -423,7 +426,17 @@ sweep_quad_kernel(const SweepParams p) {
     auto load_table = [&](unsigned base) {
         if constexpr (kRec) {
             const float4 K = kEarlyKeys ? knext : lds128(base);
-            const float4 FX = lds128(base + 16), FY = lds128(base + 32), FXY = lds128(base + 48);
+            const float4 FX = lds128(base + 16), FY = lds128(base + 32);
+            // fx * fy: read from the record, or -- where the FP32 pipe has room and the shared-memory data path does not
+            // (the correlation modes: 16 of a warp's ~20 wavefronts per plane are these table reads) -- formed again
+            // here, the same IEEE product of the same two operands
+            float4 FXY;
+            if constexpr (kFxyLocal) {
+                const float2 lo = __fmul2_rn(f2(FX.x, FX.y), f2(FY.x, FY.y)), hi = __fmul2_rn(f2(FX.z, FX.w), f2(FY.z, FY.w));
+                FXY = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+                FXY = lds128(base + 48);
+            }
             const float kk[4] = {K.x, K.y, K.z, K.w}, fx[4] = {FX.x, FX.y, FX.z, FX.w}, fy[4] = {FY.x, FY.y, FY.z, FY.w},
                         fxy[4] = {FXY.x, FXY.y, FXY.z, FXY.w};
 #pragma unroll
