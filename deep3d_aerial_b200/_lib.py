@@ -28,10 +28,11 @@ class CostVolumeArgs(C.Structure):
         ("struct_size", C.c_uint32), ("mode", C.c_int32), ("num_views", C.c_int32), ("channels", C.c_int32),
         ("height", C.c_int32), ("width", C.c_int32), ("num_depth", C.c_int32),
         ("d_begin", C.c_int32), ("d_count", C.c_int32), ("hyps_per_pixel", C.c_int32),
-        ("groups", C.c_int32), ("eps_in_numerator", C.c_int32), ("variant", C.c_int32), ("reserved0", C.c_int32),
+        ("groups", C.c_int32), ("eps_in_numerator", C.c_int32), ("variant", C.c_int32), ("texel_slots", C.c_int32),
         ("feats", _f32p), ("pose", _f32p), ("hyps", _f32p), ("weights", _f32p), ("out", _f32p),
         ("out_stride_c", C.c_int64), ("out_stride_d", C.c_int64),
         ("rays", _f32p),
+        ("view_slot", C.c_int32 * 9), ("reserved1", C.c_int32),
     ]
 
 

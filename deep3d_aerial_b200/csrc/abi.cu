@@ -133,6 +133,22 @@ extern "C" int d3d_cost_volume(const D3dCostVolumeArgs* a, void* cuda_stream) {
     p.inv_half_w = 1.f / ((float)(a->width - 1) / 2.f);
     p.inv_half_h = 1.f / ((float)(a->height - 1) / 2.f);
     p.wm1 = (float)(a->width - 1); p.hm1 = (float)(a->height - 1);
+    // where each view starts in `feats` (texel index): the dense block, or slots of a texel pool
+    p.pooled = 0;
+    for (int v = 0; v <= kMaxSrc; ++v) p.view_tex[v] = 0;
+    if (a->texel_slots < 0) return fail(D3D_ERR_BAD_ARGUMENT, "d3d_cost_volume: texel_slots %d < 0", a->texel_slots);
+    for (int v = 0; v <= nv; ++v) {
+        int slot = v;
+        if (a->texel_slots > 0) {
+            slot = a->view_slot[v];
+            if (slot < 0 || slot >= a->texel_slots)
+                return fail(D3D_ERR_BAD_ARGUMENT, "d3d_cost_volume: view_slot[%d] = %d outside the pool of %d", v, slot, a->texel_slots);
+            if (slot != v) p.pooled = 1;
+        }
+        const long long start = (long long)slot * p.HW;
+        if (start + p.HW > INT32_MAX) return fail(D3D_ERR_UNSUPPORTED, "d3d_cost_volume: texel pool beyond 2^31 texels (slot %d)", slot);
+        p.view_tex[v] = (int)start;
+    }
 
     // grid: x = pixel tiles (8 warps x 32/LPP pixels), y = depth chunks.  Depth is only split when
     // the pixel tiles alone leave SMs idle (each chunk re-warms its footprint registers).

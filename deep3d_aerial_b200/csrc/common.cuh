@@ -32,6 +32,10 @@ struct SweepParams {
     int flags;            // bit 0: prefetch moved footprints one pass ahead
     float inv_half_w, inv_half_h;  // 1/((W-1)/2), 1/((H-1)/2)   (module.py:543-544)
     float wm1, hm1;                // W-1, H-1                   (GridSampler.h:27-32)
+    // where view v starts in `feats`, as a texel index (slot * H*W): v * H*W for the dense [V,H,W,C] layout, anything else when
+    // `feats` is a texel pool [S,H,W,C] and the views are named by slot (D3dCostVolumeArgs.texel_slots)
+    int view_tex[kMaxSrc + 1];
+    int pooled;                    // 1: view_tex is not the dense layout (kernels that address views by stride refuse)
 };
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember the size each kernel was opted

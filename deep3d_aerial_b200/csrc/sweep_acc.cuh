@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kAccThreads, MB) sweep_acc_kernel(const SweepP
     const int c0 = blockIdx.z * CPL;
 
     float2 rf[NJ];
-    ldg8<CPL>(rf, p.feats + (size_t)pix * C + c0);
+    ldg8<CPL>(rf, p.feats + ((size_t)p.view_tex[0] + pix) * C + c0);
     float depth[KP];                                       // planes past the chunk's end repeat the last one (not stored)
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
@@ -82,7 +82,6 @@ __global__ void __launch_bounds__(kAccThreads, MB) sweep_acc_kernel(const SweepP
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[k][j] = splat(p.eps_num ? 1e-5f : 0.f);
 
-    const size_t view_stride = (size_t)p.HW * C;
     const int wmax = p.W - 1, hmax = p.H - 1;
     const size_t row = (size_t)p.W * C;
     // rays and translation of view v (module.py:538-541)
@@ -102,7 +101,7 @@ __global__ void __launch_bounds__(kAccThreads, MB) sweep_acc_kernel(const SweepP
     for (int v = 0; v < nv; ++v) {
         load_view(v);
         const float wt = __ldg(p.weights + (size_t)v * p.HW + pix);
-        const float* vf = p.feats + (size_t)(v + 1) * view_stride + c0;
+        const float* vf = p.feats + (size_t)p.view_tex[v + 1] * C + c0;
         unsigned ckey = 0x7fff7fffu;                       // no footprint yet (x0 = y0 = 32767 cannot occur)
         float2 A[NJ], B[NJ], Cc[NJ], D[NJ];
 #pragma unroll

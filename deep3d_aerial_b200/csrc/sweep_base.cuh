@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) sweep_base_kernel(const SweepParams p) {
 
     float rf[CPT];
     {
-        const float* t = p.feats + (size_t)pix * p.C + choff;
+        const float* t = p.feats + ((size_t)p.view_tex[0] + pix) * p.C + choff;
 #pragma unroll
         for (int k = 0; k < CPT; k += 4) {
             float4 q = ldg4(t + k);
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) sweep_base_kernel(const SweepParams p) {
         for (int v = 0; v < NV; ++v) {
             Footprint f = project<true>(rx[v], ry[v], rz[v], tx[v], ty[v], tz[v], depth, p);
             if (f.x0 != cx[v] || f.y0 != cy[v]) {
-                const float* view = p.feats + (size_t)(v + 1) * p.HW * p.C;
+                const float* view = p.feats + (size_t)p.view_tex[v + 1] * p.C;
                 load_texel<CPT>(tex[v][0], view, f.x0, f.y0, p, choff);
                 load_texel<CPT>(tex[v][1], view, f.x0 + 1, f.y0, p, choff);
                 load_texel<CPT>(tex[v][2], view, f.x0, f.y0 + 1, p, choff);

@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(256, 3) sweep_direct_kernel(const SweepParams 
     }
     float2 rf[4];
     {
-        const float4 a = ldg4(p.feats + (size_t)pix * C), b = ldg4(p.feats + (size_t)pix * C + 4);
+        const float* rt = p.feats + ((size_t)p.view_tex[0] + pix) * C;
+        const float4 a = ldg4(rt), b = ldg4(rt + 4);
         rf[0] = f2(a.x, a.y); rf[1] = f2(a.z, a.w); rf[2] = f2(b.x, b.y); rf[3] = f2(b.z, b.w);
     }
     float wt[NV];
@@ -66,7 +67,6 @@ __global__ void __launch_bounds__(256, 3) sweep_direct_kernel(const SweepParams 
     const size_t hyp_stride = kPerPix ? (size_t)p.HW : 1;
     const float* hp = p.hyps + (kPerPix ? (size_t)pix : 0) + (size_t)d0 * hyp_stride;
     float* optr = p.out + (size_t)(d0 - p.d_begin) * p.out_sd + pix;
-    const size_t view_stride = (size_t)p.HW * C;
 
     for (int dd = d0; dd < d1; ++dd, hp += hyp_stride, optr += p.out_sd) {
         const float depth = __ldg(hp);
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256, 3) sweep_direct_kernel(const SweepParams 
             const int x0 = (int)(key & 0x3fffu) - 4, y0 = (int)((key >> 14) & 0x3fffu) - 4;
             const bool xa = (unsigned)x0 < (unsigned)p.W, xb = (unsigned)(x0 + 1) < (unsigned)p.W;
             const bool ya = (unsigned)y0 < (unsigned)p.H, yb = (unsigned)(y0 + 1) < (unsigned)p.H;
-            const float* t = p.feats + (size_t)(v + 1) * view_stride + ((long long)y0 * p.W + x0) * C;
+            const float* t = p.feats + ((long long)p.view_tex[v + 1] + (long long)y0 * p.W + x0) * C;
             float4 c[4][2];
             ldg8_or_zero(c[0][0], c[0][1], t, xa && ya);
             ldg8_or_zero(c[1][0], c[1][1], t + C, xb && ya);

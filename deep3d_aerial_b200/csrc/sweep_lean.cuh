@@ -429,6 +429,7 @@ constexpr size_t sweep_lean_smem_fixed() {
 
 template <int CPT, int NV, int LPP, int MODE>
 int launch_sweep_lean(const SweepParams& p, dim3 grid, cudaStream_t stream, bool ieee_div) {
+    if (p.pooled) return -1;                         // views addressed by stride here: dense [V,H,W,C] texels only
     // + the chunk's hypotheses (fronto-parallel sweeps)
     const size_t smem = sweep_lean_smem_fixed<CPT, NV, LPP>() + (p.perpix ? 0 : (size_t)(p.d_chunk + kLeanHypPad) * 4);
     if (smem > 200 * 1024) return -1;                // absurd depth chunk: let another kernel take it

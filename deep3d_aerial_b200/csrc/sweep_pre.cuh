@@ -349,6 +349,7 @@ int launch_sweep_pre(const SweepParams& p, dim3 grid, cudaStream_t stream) {
 
 // returns -1 when the shape is not covered (the caller falls back to sweep_quad)
 inline int sweep_pre_dispatch(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream) {
+    if (p.pooled) return -1;                         // views addressed by stride here: dense [V,H,W,C] texels only
     if (p.W > 16000 || p.H > 16000) return -1;       // 15-bit corner fields in the table entry
     if (p.C != 32 || (p.HW & 31) != 0) return -1;
     if (((p.out_sc | p.out_sd) & 3) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return -1;

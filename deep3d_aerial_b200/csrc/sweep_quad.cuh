@@ -38,24 +38,24 @@ __host__ __device__ constexpr int quad_dot_rows(int mode, int gs, int c) {
 template <int NV, int TEXB, int V = 0>
 struct RefetchTok {
     static __device__ __forceinline__ void run(float2 (&tex)[NV][4][2], unsigned (&ckey)[NV], const float4 (&g)[NV],
-                                               const float* base, unsigned row_bytes, int hw, int W, int H) {
-        refetch_tok<V + 1, TEXB>(tex[V], ckey[V], __float_as_uint(g[V].w), base, row_bytes, hw, W, H);
-        RefetchTok<NV, TEXB, V + 1>::run(tex, ckey, g, base, row_bytes, hw, W, H);
+                                               const float* base, unsigned row_bytes, const int (&vt)[kMaxSrc + 1], int W, int H) {
+        refetch_tok<V + 1, TEXB>(tex[V], ckey[V], __float_as_uint(g[V].w), base, row_bytes, vt[V + 1], W, H);
+        RefetchTok<NV, TEXB, V + 1>::run(tex, ckey, g, base, row_bytes, vt, W, H);
     }
     // variance volume of the long sweeps: A = a - ref (the reference view then contributes nothing to sum / sum of squares)
     static __device__ __forceinline__ void run_shift(float2 (&tex)[NV][4][2], unsigned (&ckey)[NV], const float4 (&g)[NV],
-                                                     const float* base, unsigned row_bytes, int hw, int W, int H,
+                                                     const float* base, unsigned row_bytes, const int (&vt)[kMaxSrc + 1], int W, int H,
                                                      const float2 (&ref)[2]) {
-        refetch_tok_shift<V + 1, TEXB>(tex[V], ckey[V], __float_as_uint(g[V].w), base, row_bytes, hw, W, H, ref);
-        RefetchTok<NV, TEXB, V + 1>::run_shift(tex, ckey, g, base, row_bytes, hw, W, H, ref);
+        refetch_tok_shift<V + 1, TEXB>(tex[V], ckey[V], __float_as_uint(g[V].w), base, row_bytes, vt[V + 1], W, H, ref);
+        RefetchTok<NV, TEXB, V + 1>::run_shift(tex, ckey, g, base, row_bytes, vt, W, H, ref);
     }
 };
 template <int NV, int TEXB>
 struct RefetchTok<NV, TEXB, NV> {
     static __device__ __forceinline__ void run(float2 (&)[NV][4][2], unsigned (&)[NV], const float4 (&)[NV], const float*,
-                                               unsigned, int, int, int) {}
+                                               unsigned, const int (&)[kMaxSrc + 1], int, int) {}
     static __device__ __forceinline__ void run_shift(float2 (&)[NV][4][2], unsigned (&)[NV], const float4 (&)[NV], const float*,
-                                                     unsigned, int, int, int, const float2 (&)[2]) {}
+                                                     unsigned, const int (&)[kMaxSrc + 1], int, int, const float2 (&)[2]) {}
 };
 
 // The same in two phases (issue_tok / rebuild_tok): every moved view's loads are started before any view is rebuilt,
@@ -63,15 +63,15 @@ struct RefetchTok<NV, TEXB, NV> {
 template <int NV, int TEXB, int V = 0>
 struct RefetchIssue {
     static __device__ __forceinline__ void run(float2 (&tex)[NV][4][2], unsigned (&ckey)[NV], unsigned& mv, const float4 (&g)[NV],
-                                               const float* base, unsigned row_bytes, int hw, int W, int H) {
-        issue_tok<V + 1, TEXB>(tex[V], ckey[V], mv, __float_as_uint(g[V].w), base, row_bytes, hw, W, H);
-        RefetchIssue<NV, TEXB, V + 1>::run(tex, ckey, mv, g, base, row_bytes, hw, W, H);
+                                               const float* base, unsigned row_bytes, const int (&vt)[kMaxSrc + 1], int W, int H) {
+        issue_tok<V + 1, TEXB>(tex[V], ckey[V], mv, __float_as_uint(g[V].w), base, row_bytes, vt[V + 1], W, H);
+        RefetchIssue<NV, TEXB, V + 1>::run(tex, ckey, mv, g, base, row_bytes, vt, W, H);
     }
 };
 template <int NV, int TEXB>
 struct RefetchIssue<NV, TEXB, NV> {
     static __device__ __forceinline__ void run(float2 (&)[NV][4][2], unsigned (&)[NV], unsigned&, const float4 (&)[NV],
-                                               const float*, unsigned, int, int, int) {}
+                                               const float*, unsigned, const int (&)[kMaxSrc + 1], int, int) {}
 };
 template <int NV, int V = 0>
 struct RefetchRebuild {
@@ -90,16 +90,16 @@ struct RefetchRebuild<NV, NV> {
 template <int NV, int TEXB, int V = 0>
 struct RefetchDot {
     static __device__ __forceinline__ void run(float (&dot)[NV][4], unsigned (&ckey)[NV], const float4 (&g)[NV],
-                                               const float* base, unsigned row_bytes, int hw, int W, int H,
+                                               const float* base, unsigned row_bytes, const int (&vt)[kMaxSrc + 1], int W, int H,
                                                const float (&ref)[4]) {
-        refetch_dot<V + 1, TEXB>(dot[V], ckey[V], __float_as_uint(g[V].w), base, row_bytes, hw, W, H, ref);
-        RefetchDot<NV, TEXB, V + 1>::run(dot, ckey, g, base, row_bytes, hw, W, H, ref);
+        refetch_dot<V + 1, TEXB>(dot[V], ckey[V], __float_as_uint(g[V].w), base, row_bytes, vt[V + 1], W, H, ref);
+        RefetchDot<NV, TEXB, V + 1>::run(dot, ckey, g, base, row_bytes, vt, W, H, ref);
     }
 };
 template <int NV, int TEXB>
 struct RefetchDot<NV, TEXB, NV> {
     static __device__ __forceinline__ void run(float (&)[NV][4], unsigned (&)[NV], const float4 (&)[NV], const float*, unsigned,
-                                               int, int, int, const float (&)[4]) {}
+                                               const int (&)[kMaxSrc + 1], int, int, const float (&)[4]) {}
 };
 
 // MODE: D3D_AGG_VARIANCE, D3D_AGG_WEIGHTED_PRODUCT (both write C rows per plane) or D3D_AGG_GROUP_CORR
@@ -195,7 +195,7 @@ sweep_quad_kernel(const SweepParams p) {
             }
             tx[i] = m[3]; ty[i] = m[7]; tz[i] = m[11];
         }
-        const float4 w = ldg4(p.feats + (size_t)pix * C + choff);
+        const float4 w = ldg4(p.feats + ((size_t)p.view_tex[0] + pix) * C + choff);
         rf[0] = f2(w.x, w.y);
         rf[1] = f2(w.z, w.w);
         rf2[0] = __fmul2_rn(rf[0], rf[0]);                 // variance: ref^2 once per pixel, not once per plane
@@ -463,15 +463,15 @@ sweep_quad_kernel(const SweepParams p) {
             for (int v = 0; v < NV; ++v) moved |= __float_as_uint(g[v].w) ^ ckey[v];
             if (moved) {                             // some footprint moved: re-fetch those (in place)
                 if constexpr (kDot) {
-                    RefetchDot<NV, C * 4>::run(dotc, ckey, g, feats_c, row_bytes, p.HW, p.W, p.H, rfs);
+                    RefetchDot<NV, C * 4>::run(dotc, ckey, g, feats_c, row_bytes, p.view_tex, p.W, p.H, rfs);
                 } else if constexpr (kSplit) {
                     unsigned mv = 0;
-                    RefetchIssue<NV, C * 4>::run(tex, ckey, mv, g, feats_c, row_bytes, p.HW, p.W, p.H);
+                    RefetchIssue<NV, C * 4>::run(tex, ckey, mv, g, feats_c, row_bytes, p.view_tex, p.W, p.H);
                     RefetchRebuild<NV>::run(tex, mv);
                 } else if constexpr (kShift) {
-                    RefetchTok<NV, C * 4>::run_shift(tex, ckey, g, feats_c, row_bytes, p.HW, p.W, p.H, rf);
+                    RefetchTok<NV, C * 4>::run_shift(tex, ckey, g, feats_c, row_bytes, p.view_tex, p.W, p.H, rf);
                 } else {
-                    RefetchTok<NV, C * 4>::run(tex, ckey, g, feats_c, row_bytes, p.HW, p.W, p.H);
+                    RefetchTok<NV, C * 4>::run(tex, ckey, g, feats_c, row_bytes, p.view_tex, p.W, p.H);
                 }
             }
             if constexpr (kEarlyKeys) {

@@ -290,6 +290,7 @@ int launch_sweep_win(int nv, const SweepParams& p, cudaStream_t stream, bool iee
 
 // returns -1 when the shape is not covered
 inline int sweep_win_dispatch(int nv, const SweepParams& p, cudaStream_t stream, bool ieee_div) {
+    if (p.pooled) return -1;                         // views addressed by stride here: dense [V,H,W,C] texels only
     if (p.W > 16000 || p.H > 16000 || nv < 1 || !p.weights) return -1;
     if (reinterpret_cast<uintptr_t>(p.feats) & 31) return -1;      // 256-bit texel loads, 16-byte TMA rows
     if (p.C == 8) return (p.flags & 1) ? launch_sweep_win<8, 4, 4>(nv, p, stream, ieee_div) : launch_sweep_win<8, 8, 3>(nv, p, stream, ieee_div);

@@ -421,6 +421,7 @@ int launch_sweep_ws(const SweepParams& p, dim3 grid, cudaStream_t stream) {
 // returns -1 when the shape is not covered (the caller falls back to sweep_quad / sweep_lean / sweep_base)
 template <int MODE>
 int sweep_ws_dispatch(int nv, const SweepParams& p, dim3 grid, cudaStream_t stream) {
+    if (p.pooled) return -1;                         // views addressed by stride here: dense [V,H,W,C] texels only
     if (p.W > 16000 || p.H > 16000) return -1;       // 15-bit corner fields in the table entry
     if (p.C != 32 || (p.HW & 31) != 0) return -1;
     if ((unsigned long long)(nv + 1) * (unsigned long long)p.HW >= (1ull << 25)) return -1;   // 32-bit byte offsets into `feats`

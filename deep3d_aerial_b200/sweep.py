@@ -163,8 +163,12 @@ def cost_volume(texels: torch.Tensor, pose: torch.Tensor, hyps: torch.Tensor, mo
                 groups: int = 0, weights: Optional[torch.Tensor] = None, eps_in_numerator: bool = False,
                 d_begin: int = 0, d_count: int = 0, out: Optional[torch.Tensor] = None,
                 plane_major: bool = False, variant: int = 0, rays: Optional[torch.Tensor] = None,
-                exact_rays: bool = True) -> torch.Tensor:
+                exact_rays: bool = True, view_slots=None) -> torch.Tensor:
     """Fused warp + aggregate.  texels [V,H,W,C]; pose [V-1,4,4]; hyps [D] or [D,H,W].
+
+    view_slots: `texels` is then a POOL [S,H,W,C] of per-image maps (laid out once per image, `to_texels(..., out=pool[s])`)
+    and view v of this sweep is pool slot view_slots[v] (v = 0: the reference) -- the reference views of a scene block share
+    their images, so nothing is relaid out or copied per view.
 
     rays: `rays_for(pose, H, W)` if the caller already has them (plane-slice callers compute them once per view);
     with exact_rays (default) that call is made here -- the reference's own matmul wherever the kernel's rounding
@@ -177,6 +181,12 @@ def cost_volume(texels: torch.Tensor, pose: torch.Tensor, hyps: torch.Tensor, mo
     pose = _need(pose, "pose")
     hyps = _need(hyps, "hyps")
     v, h, w, c = texels.shape
+    slots = None
+    if view_slots is not None:                    # `texels` is a pool [S,h,w,c] of per-image maps; the views are named by slot
+        slots = [int(x) for x in view_slots]
+        if not 2 <= len(slots) <= 9 or any(x < 0 or x >= v for x in slots):
+            raise ValueError("view_slots must name 2..9 slots of the %d-slot texel pool, got %s" % (v, slots))
+        pool_slots, v = v, len(slots)
     if tuple(pose.shape) != (v - 1, 4, 4):
         raise ValueError("pose must be [%d,4,4], got %s" % (v - 1, tuple(pose.shape)))
     if hyps.dim() == 1:
@@ -209,6 +219,10 @@ def cost_volume(texels: torch.Tensor, pose: torch.Tensor, hyps: torch.Tensor, mo
     a.mode, a.num_views, a.channels, a.height, a.width, a.num_depth = mode, v, c, h, w, d
     a.d_begin, a.d_count, a.hyps_per_pixel = d_begin, dn, per_pixel
     a.groups, a.eps_in_numerator, a.variant = groups, int(eps_in_numerator), variant
+    if slots is not None:
+        a.texel_slots = pool_slots
+        for i, x in enumerate(slots):
+            a.view_slot[i] = x
     if rays is None and exact_rays:
         rays = rays_for(pose, h, w)
     if rays is not None:

@@ -70,8 +70,11 @@ typedef struct D3dCostVolumeArgs {
     int32_t groups;           /* G for D3D_AGG_GROUP_CORR (C % G == 0)                            */
     int32_t eps_in_numerator; /* D3D_AGG_WEIGHTED_PRODUCT: training-form epsilon placement        */
     int32_t variant;          /* 0 = production kernel; others select A/B kernels */
-    int32_t reserved0;
-    const float* feats;       /* [V,H,W,C] channels-last, view 0 = reference (d3d_nchw_to_nhwc)   */
+    int32_t texel_slots;      /* 0: `feats` is the dense [V,H,W,C] block of this reference view.  S > 0: `feats` is a
+                                 texel POOL [S,H,W,C] of per-image maps and view v lives in slot view_slot[v] -- the
+                                 images of a scene block are laid out once (d3d_nchw_to_nhwc per IMAGE) and every
+                                 reference view names the five it uses (adamvs.py:570-574 re-encodes them per view) */
+    const float* feats;       /* [V,H,W,C] channels-last, view 0 = reference (d3d_nchw_to_nhwc); or the pool       */
     const float* pose;        /* [V-1,4,4] row-major P_src @ inverse(P_ref), module.py:528-530    */
     const float* hyps;        /* depth hypotheses, see hyps_per_pixel                             */
     const float* weights;     /* [V-1,H,W] view weights (WEIGHTED_PRODUCT only), already at H x W  */
@@ -85,6 +88,8 @@ typedef struct D3dCostVolumeArgs {
                                  fma(r2,1,fma(r1,y,r0*x)), the order cuBLAS uses for most -- not all --
                                  problem sizes (Numerics).  Passing them makes the sample
                                  coordinates bit-identical to the reference's at every size           */
+    int32_t view_slot[9];     /* texel_slots > 0: pool slot of view v (v = 0: the reference), each < texel_slots  */
+    int32_t reserved1;
 } D3dCostVolumeArgs;
 
 /* Fused homography warp + bilinear sample + aggregation; the V x C x D x H x W warped volume is

@@ -71,6 +71,13 @@ def test_validation_errors_need_no_gpu(lib):
     a.num_views = 3
     a.d_begin, a.d_count = 3, 5
     assert lib.d3d_cost_volume(C.byref(a), None) == _lib.ERR_BAD_ARGUMENT    # slice outside the sweep
+    a.d_begin, a.d_count = 0, 0
+    a.texel_slots = 4                              # views named as slots of a texel pool: every slot must be inside it
+    a.view_slot[0], a.view_slot[1], a.view_slot[2] = 3, 0, 4
+    assert lib.d3d_cost_volume(C.byref(a), None) == _lib.ERR_BAD_ARGUMENT
+    assert b"view_slot[2]" in lib.d3d_last_error()
+    a.texel_slots = -1
+    assert lib.d3d_cost_volume(C.byref(a), None) == _lib.ERR_BAD_ARGUMENT
     r = _lib.RegressArgs()
     r.struct_size = C.sizeof(r)
     r.num_depth, r.height, r.width = 4, 4, 4

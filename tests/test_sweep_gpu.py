@@ -885,3 +885,59 @@ def test_resize_pair_weights_stacks_and_falls_through():
         torch.testing.assert_close(r, w, rtol=1e-6, atol=1e-6)
     same, wsame = depthnets._resize_pair_weights(maps, 4, 20, 30)                     # stage 1: same size, values untouched
     assert all(torch.equal(a, b) for a, b in zip(same, maps[:4])) and torch.equal(wsame, torch.cat(maps[:4], 1))
+
+
+# ------------------------------------------------------- texel pool: views named by slot (D3dCostVolumeArgs.texel_slots)
+_POOL_CASES = [
+    # v, c, d, h, w, mode, kwargs, per-pixel hypotheses
+    (5, 32, 136, 16, 32, sweep.AGG_VARIANCE, {}, False),                 # sweep_quad, one-block re-fetch, shifted footprints
+    (5, 32, 12, 16, 32, sweep.AGG_VARIANCE, {}, True),                   # sweep_quad, two-phase re-fetch
+    (5, 32, 136, 16, 32, sweep.AGG_GROUP_CORR, {"groups": 8}, False),    # corner dot products
+    (5, 32, 12, 16, 32, sweep.AGG_GROUP_CORR, {"groups": 32}, False),    # coefficient cache
+    (5, 32, 12, 16, 32, sweep.AGG_PAIR_MEAN, {}, True),
+    (4, 32, 12, 16, 32, sweep.AGG_WEIGHTED_PRODUCT, {"weights": True}, True),
+    (5, 16, 12, 16, 32, sweep.AGG_WEIGHTED_PRODUCT, {"weights": True}, True),   # four lanes per pixel
+    (3, 16, 12, 16, 32, sweep.AGG_VARIANCE, {}, False),
+    (5, 8, 8, 16, 32, sweep.AGG_WEIGHTED_PRODUCT, {"weights": True}, True),     # sweep_acc
+    (3, 8, 12, 16, 32, sweep.AGG_VARIANCE, {}, False),                   # sweep_direct
+    (7, 8, 6, 12, 20, sweep.AGG_VARIANCE, {}, False),                    # sweep_base (six source views)
+    (2, 4, 6, 12, 20, sweep.AGG_WARP, {}, False),                        # sweep_base, the plain warp
+    (3, 64, 6, 16, 32, sweep.AGG_VARIANCE, {}, False),                   # sweep_lean's shape: refuses the pool, sweep_base takes it
+]
+
+
+@pytest.mark.parametrize("v,c,d,h,w,mode,kw,perpix", _POOL_CASES)
+def test_texel_pool_slots_match_dense_block(v, c, d, h, w, mode, kw, perpix):
+    """The views of a sweep named as slots of a per-image texel pool: bit-identical to the dense [V,H,W,C] block wherever the
+    same kernel serves both (every production kernel), and within the volume tolerance where the pool falls through to
+    another kernel."""
+    rig, proj, feats, hyps = _scene(v, c, d, h, w, seed=11, perpixel=perpix)
+    tex = sweep.to_texels(feats.to(DEV))
+    pose = sweep.relative_poses(proj[0].to(DEV))
+    hy = hyps[0].to(DEV).contiguous()
+    kw = dict(kw)
+    if kw.pop("weights", False):
+        kw["weights"] = torch.rand(v - 1, h, w, generator=torch.Generator().manual_seed(2)).to(DEV)
+    dense = sweep.cost_volume(tex, pose, hy, mode, **kw)
+    slots = [6, 2, 7, 0, 4, 9, 1][:v]                                    # scattered, out of order, the reference not first
+    pool = torch.full((10, h, w, c), float("nan"), device=DEV)
+    for i, s in enumerate(slots):
+        pool[s].copy_(tex[i])
+    pooled = sweep.cost_volume(pool, pose, hy, mode, view_slots=slots, **kw)
+    assert not torch.isnan(pooled).any()
+    if c == 64:
+        assert rel_norm_err(pooled.cpu(), dense.cpu()) < VOL_TOL
+    else:
+        assert torch.equal(pooled, dense)
+    # the identity naming of a pool that IS the dense block takes the dense path
+    assert torch.equal(sweep.cost_volume(tex, pose, hy, mode, view_slots=list(range(v)), **kw), dense)
+
+
+def test_texel_pool_slot_validation():
+    rig, proj, feats, hyps = _scene(3, 8, 4, 12, 20)
+    tex = sweep.to_texels(feats.to(DEV))
+    pose = sweep.relative_poses(proj[0].to(DEV))
+    with pytest.raises(ValueError, match="view_slots"):
+        sweep.cost_volume(tex, pose, hyps[0].to(DEV), view_slots=[0, 1, 3])
+    with pytest.raises(ValueError, match="pose"):
+        sweep.cost_volume(tex, pose, hyps[0].to(DEV), view_slots=[0, 1])

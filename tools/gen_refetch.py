@@ -259,7 +259,7 @@ def block_tok(cpt, shift=False):
     A("bfe.s32 x0, %%%d, 0, 16;" % key)
     A("bfe.s32 y0, %%%d, 16, 16;" % key)
     A("mad.lo.s32 t, y0, %%%d, x0;" % wid)
-    A("mad.lo.s32 t, %%%d, %%%d, t;" % (hw, vplus1))
+    A("add.s32 t, t, %%%d;" % hw)                 # + the texel index at which this view starts in `base` (SweepParams.view_tex)
     A("mad.wide.s32 pa, t, %%%d, %%%d;" % (texb, base))
     A("cvt.u64.u32 w, %%%d;" % rowb)
     A("add.s64 pc, pa, w;")
@@ -309,11 +309,11 @@ def block_tok(cpt, shift=False):
         return """// Token-keyed re-fetch with the reference texel subtracted from A (variance volume, long sweeps): see block_tok.
 template <int VPLUS1, int TEXEL_BYTES>
 __device__ __forceinline__ void refetch_tok_shift(float2 (&t)[4][%d], unsigned& cur_key, unsigned key, const float* base,
-                                                  unsigned row_bytes, int hw, int width, int height, const float2 (&ref)[%d]) {
+                                                  unsigned row_bytes, int view_tex, int width, int height, const float2 (&ref)[%d]) {
     asm volatile(
         %s
         : %s
-        : "r"(key), "l"(base), "r"(row_bytes), "r"(hw), "r"(width), "r"(height), "r"(width - 1), "r"(height - 1),
+        : "r"(key), "l"(base), "r"(row_bytes), "r"(view_tex), "r"(width), "r"(height), "r"(width - 1), "r"(height - 1),
           "n"(VPLUS1), "n"(TEXEL_BYTES), "n"(TEXEL_BYTES + 16), %s);
 }
 """ % (cpt // 2, cpt // 2, body, outs, refs)
@@ -323,11 +323,11 @@ __device__ __forceinline__ void refetch_tok_shift(float2 (&t)[4][%d], unsigned& 
 // the rebuild of A, B, C, D -- happens here, on the rare path.  `cur_key` is updated in place.
 template <int VPLUS1, int TEXEL_BYTES>
 __device__ __forceinline__ void refetch_tok(float2 (&t)[4][%d], unsigned& cur_key, unsigned key, const float* base,
-                                            unsigned row_bytes, int hw, int width, int height) {
+                                            unsigned row_bytes, int view_tex, int width, int height) {
     asm volatile(
         %s
         : %s
-        : "r"(key), "l"(base), "r"(row_bytes), "r"(hw), "r"(width), "r"(height), "r"(width - 1), "r"(height - 1),
+        : "r"(key), "l"(base), "r"(row_bytes), "r"(view_tex), "r"(width), "r"(height), "r"(width - 1), "r"(height - 1),
           "n"(VPLUS1), "n"(TEXEL_BYTES), "n"(TEXEL_BYTES + 16));
 }
 """ % (cpt // 2, body, outs)
@@ -354,7 +354,7 @@ def block_tok_split(cpt):
     A("bfe.s32 x0, %%%d, 0, 16;" % key)
     A("bfe.s32 y0, %%%d, 16, 16;" % key)
     A("mad.lo.s32 t, y0, %%%d, x0;" % wid)
-    A("mad.lo.s32 t, %%%d, %%%d, t;" % (hw, vplus1))
+    A("add.s32 t, t, %%%d;" % hw)                 # + the texel index at which this view starts in `base` (SweepParams.view_tex)
     A("mad.wide.s32 pa, t, %%%d, %%%d;" % (texb, base))
     A("cvt.u64.u32 w, %%%d;" % rowb)
     A("add.s64 pc, pa, w;")
@@ -401,11 +401,11 @@ def block_tok_split(cpt):
 // `cur_key` and set bit VPLUS1 of `moved`.
 template <int VPLUS1, int TEXEL_BYTES>
 __device__ __forceinline__ void issue_tok(float2 (&t)[4][%d], unsigned& cur_key, unsigned& moved, unsigned key,
-                                          const float* base, unsigned row_bytes, int hw, int width, int height) {
+                                          const float* base, unsigned row_bytes, int view_tex, int width, int height) {
     asm volatile(
         %s
         : %s
-        : "r"(key), "l"(base), "r"(row_bytes), "r"(hw), "r"(width), "r"(height), "r"(width - 1), "r"(height - 1),
+        : "r"(key), "l"(base), "r"(row_bytes), "r"(view_tex), "r"(width), "r"(height), "r"(width - 1), "r"(height - 1),
           "n"(VPLUS1), "n"(TEXEL_BYTES), "n"(TEXEL_BYTES + 16));
 }
 """ % (cpt // 2, body, outs)
@@ -546,7 +546,7 @@ def block_dot(cpt):
     A("bfe.s32 x0, %%%d, 0, 16;" % key)
     A("bfe.s32 y0, %%%d, 16, 16;" % key)
     A("mad.lo.s32 t, y0, %%%d, x0;" % wid)
-    A("mad.lo.s32 t, %%%d, %%%d, t;" % (hw, vplus1))
+    A("add.s32 t, t, %%%d;" % hw)                 # + the texel index at which this view starts in `base` (SweepParams.view_tex)
     A("mad.wide.s32 pa, t, %%%d, %%%d;" % (texb, base))
     A("cvt.u64.u32 w, %%%d;" % rowb)
     A("add.s64 pc, pa, w;")
@@ -590,11 +590,11 @@ def block_dot(cpt):
 // PD} of this lane's %d channels against the reference texel `ref`; `cur_key` is updated in place.
 template <int VPLUS1, int TEXEL_BYTES>
 __device__ __forceinline__ void refetch_dot(float (&dot)[4], unsigned& cur_key, unsigned key, const float* base,
-                                            unsigned row_bytes, int hw, int width, int height, const float (&ref)[%d]) {
+                                            unsigned row_bytes, int view_tex, int width, int height, const float (&ref)[%d]) {
     asm volatile(
         %s
         : "+f"(dot[0]), "+f"(dot[1]), "+f"(dot[2]), "+f"(dot[3]), "+r"(cur_key)
-        : "r"(key), "l"(base), "r"(row_bytes), "r"(hw), "r"(width), "r"(height), "r"(width - 1), "r"(height - 1),
+        : "r"(key), "l"(base), "r"(row_bytes), "r"(view_tex), "r"(width), "r"(height), "r"(width - 1), "r"(height - 1),
           "n"(VPLUS1), "n"(TEXEL_BYTES), "n"(TEXEL_BYTES + 16), %s);
 }
 """ % (cpt, cpt, body, ", ".join('"f"(ref[%d])' % c for c in range(cpt)))
