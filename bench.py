@@ -381,8 +381,10 @@ def e2e_block(args, wl, dev, rank, slots, views, n_block, warm_views=2):
             "h2d_bytes_per_step_without_image_residency": pipe.h2d_bytes,
             "ms_per_step": dt / done * 1e3, "steps": len(views), "timer": "host wall clock around submit/collect",
             "stream": "a scene block walked in order (viewpair windows of %d consecutive images): a view uploads only "
-                      "the images not yet resident on its GPU (LRU of %d per-image feature maps); the first view of "
-                      "the timed block uploads all %d" % (v, 3 * v, v),
+                      "the images not yet resident on its GPU (LRU of %d per-image maps kept as channels-last texels: an "
+                      "image is laid out once, when it arrives, and the sweep names its views by pool slot, whereas the "
+                      "device-timed `value` step lays out all %d maps of its view); the first view of the timed block "
+                      "uploads all %d" % (v, 3 * v, v, v),
             "image_hits": pipe.lru.hits, "image_misses": pipe.lru.misses}
 
 

@@ -19,6 +19,9 @@ view).  When the caller names the images of a view, their feature maps stay on t
 image id and a view uploads only the images that are not there yet -- 41 MB instead of 204 MB at the WHU-OMVS
 shape, which is what makes the end-to-end number scale across the 8 GPUs of a box (the host->device copies of
 8 ranks share the host's memory system: SCALE_r01 measured 22 GB/s per rank at N = 8 against 34 GB/s at N = 1).
+The resident images are kept as channels-last TEXELS (`ImageFeatureLRU(texels=True)`): an image is laid out once, when
+it arrives, on the copy stream, and the sweep names its five views by pool slot (`sweep.cost_volume(..., view_slots=)`,
+D3dCostVolumeArgs.texel_slots) -- no relayout and no gather copy per reference view.
 """
 from __future__ import annotations
 
@@ -35,11 +38,22 @@ class ImageFeatureLRU:
     device tensor of an image, copying it from the host (on the current stream) only on a miss; a buffer is not
     refilled before the stream that last read it has passed the event the reader recorded (`mark_read`)."""
 
-    def __init__(self, capacity: int, channels: int, height: int, width: int, device):
+    def __init__(self, capacity: int, channels: int, height: int, width: int, device, texels: bool = False):
+        """texels: keep the images as channels-last TEXELS [capacity,H,W,C] -- the layout the sweep kernels gather from --
+        laid out once, when an image arrives (`fetch_slot`); a sweep then names its views by pool slot
+        (`sweep.cost_volume(lru.texels, ..., view_slots=...)`) and nothing is relaid out or copied per reference view."""
         if capacity < 1:
             raise ValueError("capacity must be >= 1")
         self.capacity = capacity
-        self.pool = torch.empty((capacity, channels, height, width), device=device)
+        self.texels = None
+        if texels:
+            if capacity * height * width >= 2 ** 31:
+                raise ValueError("texel pool of %d x %d x %d exceeds 2^31 texels" % (capacity, height, width))
+            self.texels = torch.empty((capacity, height, width, channels), device=device)
+            self.pool = None
+            self._staging = torch.empty((channels, height, width), device=device)     # one upload at a time, in stream order
+        else:
+            self.pool = torch.empty((capacity, channels, height, width), device=device)
         self.free = list(range(capacity))
         self.slot_of = collections.OrderedDict()          # image id -> pool slot, oldest first
         self.read_done = [None] * capacity                # event after the last reader of each slot
@@ -48,11 +62,16 @@ class ImageFeatureLRU:
 
     def fetch(self, image_id, host_map: torch.Tensor, pinned: Sequence = ()) -> torch.Tensor:
         """`pinned`: ids that must survive this call (the other images of the view being assembled)."""
+        slot = self.fetch_slot(image_id, host_map, pinned)
+        return self.pool[slot] if self.texels is None else self.texels[slot]
+
+    def fetch_slot(self, image_id, host_map: torch.Tensor, pinned: Sequence = ()) -> int:
+        """The pool slot of an image, uploaded (and, in texel mode, laid out channels-last) on the current stream on a miss."""
         slot = self.slot_of.get(image_id)
         if slot is not None:
             self.slot_of.move_to_end(image_id)
             self.hits += 1
-            return self.pool[slot]
+            return slot
         self.misses += 1
         if self.free:
             slot = self.free.pop()
@@ -63,10 +82,17 @@ class ImageFeatureLRU:
             slot = self.slot_of.pop(victim)
             if self.read_done[slot] is not None:          # the sweep that last read this buffer must be past it
                 torch.cuda.current_stream().wait_event(self.read_done[slot])
-        self.pool[slot].copy_(host_map, non_blocking=True)
+        if self.texels is None:
+            self.pool[slot].copy_(host_map, non_blocking=True)
+        else:                                             # upload, then the image's ONE relayout, both in stream order
+            src = host_map
+            if not host_map.is_cuda:
+                self._staging.copy_(host_map, non_blocking=True)
+                src = self._staging
+            sweep.to_texels([src], out=self.texels[slot:slot + 1])
         self.bytes_copied += host_map.numel() * host_map.element_size()
         self.slot_of[image_id] = slot
-        return self.pool[slot]
+        return slot
 
     def mark_read(self, image_ids, event) -> None:
         for k in image_ids:
@@ -78,9 +104,12 @@ class ImageFeatureLRU:
 class ViewPipeline:
     def __init__(self, num_views: int, channels: int, height: int, width: int, num_depth: int, device,
                  mode: int = sweep.AGG_VARIANCE, groups: int = 0, conf_mode: int = sweep.CONF_MAX_PROB,
-                 per_pixel_hyps: bool = False, variant: int = 0, slots: int = 2, resident_images: int = 0):
+                 per_pixel_hyps: bool = False, variant: int = 0, slots: int = 2, resident_images: int = 0,
+                 resident_texels: bool = True):
         """resident_images: capacity of the image-keyed feature LRU (0 = 3 * num_views when a submit names its
-        images).  It must hold the images of every view in flight: >= slots * num_views is always enough."""
+        images).  It must hold the images of every view in flight: >= slots * num_views is always enough.
+        resident_texels: the LRU keeps the images as channels-last texels, laid out once per image; the sweep names its
+        views by pool slot (False: per-image [C,H,W] maps, relaid out into a dense block for every reference view)."""
         self.dev = torch.device(device)
         if self.dev.type != "cuda":
             raise RuntimeError("ViewPipeline runs on CUDA only (no CPU fallback)")
@@ -91,6 +120,7 @@ class ViewPipeline:
         hyp_shape = (d, h, w) if per_pixel_hyps else (d,)
         self._hyp_elems = d * h * w if per_pixel_hyps else d
         self._resident = resident_images
+        self._resident_texels = resident_texels
         self.lru: Optional[ImageFeatureLRU] = None
         with torch.cuda.device(self.dev):
             self.copy_stream = torch.cuda.Stream()
@@ -147,11 +177,15 @@ class ViewPipeline:
                     cap = self._resident or 3 * v
                     if cap < len(self.slots) * v:
                         raise ValueError("resident_images must be >= slots * num_views = %d" % (len(self.slots) * v))
-                    self.lru = ImageFeatureLRU(cap, c, h, w, self.dev)
+                    self.lru = ImageFeatureLRU(cap, c, h, w, self.dev, texels=self._resident_texels)
                 before = self.lru.bytes_copied
                 ids = list(image_ids)
                 # the previous views in flight keep their images: an LRU of >= slots * V entries cannot reach them
-                s["maps"] = [self.lru.fetch(ids[i], feats[i], pinned=ids) for i in range(v)]
+                if self.lru.texels is not None:
+                    s["view_slots"] = [self.lru.fetch_slot(ids[i], feats[i], pinned=ids) for i in range(v)]
+                    s["maps"] = None
+                else:
+                    s["maps"] = [self.lru.fetch(ids[i], feats[i], pinned=ids) for i in range(v)]
                 s["ids"] = ids
                 copied += self.lru.bytes_copied - before
             s["proj"].copy_(proj, non_blocking=True)
@@ -165,13 +199,18 @@ class ViewPipeline:
         self.views_submitted += 1
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(s["copied"])
-            sweep.to_texels(s["maps"], out=self.texels)
-            if s["ids"] is not None:
+            if s["maps"] is None:                             # the view's images are texel-pool slots: nothing to lay out
+                sweep.cost_volume(self.lru.texels, s["pose"], s["hyps"], self.mode, groups=self.groups, out=self.volume,
+                                  variant=self.variant, rays=s["rays"], view_slots=s["view_slots"])
+            else:
+                sweep.to_texels(s["maps"], out=self.texels)
+            if s["ids"] is not None:                          # (the sweep itself is the pool's last reader)
                 read = torch.cuda.Event()
                 read.record()
                 self.lru.mark_read(s["ids"], read)
-            sweep.cost_volume(self.texels, s["pose"], s["hyps"], self.mode, groups=self.groups, out=self.volume,
-                              variant=self.variant, rays=s["rays"])
+            if s["maps"] is not None:
+                sweep.cost_volume(self.texels, s["pose"], s["hyps"], self.mode, groups=self.groups, out=self.volume,
+                                  variant=self.variant, rays=s["rays"])
             logits = logits_fn(self.volume)
             r = sweep.depth_regress(logits, s["hyps"], conf_mode=self.conf_mode, want_index=False)
             s["free"].record()                                # inputs consumed: the slot may be refilled

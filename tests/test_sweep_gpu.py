@@ -795,8 +795,9 @@ def test_view_pipeline_matches_direct_calls():
     assert pipe.h2d_bytes == 4 * (v * c * h * w + 16 * v + d) and pipe.d2h_bytes == 8 * h * w
 
 
+@pytest.mark.parametrize("texels", [True, False])
 @pytest.mark.parametrize("capacity", [15, 10])
-def test_view_pipeline_image_residency_uploads_each_image_once_and_builds_the_same_volumes(capacity):
+def test_view_pipeline_image_residency_uploads_each_image_once_and_builds_the_same_volumes(capacity, texels):
     """ViewPipeline.submit(image_ids=...): the views of a scene block share their images; feature maps of resident
     images are not copied again, evicted buffers are not refilled under a sweep that still reads them, and every view
     gets the volume of ITS images (the regulariser here reads the volume, so a wrong image shows in the depth)."""
@@ -807,7 +808,7 @@ def test_view_pipeline_image_residency_uploads_each_image_once_and_builds_the_sa
     g = torch.Generator().manual_seed(99)
     images = [torch.randn(c, h, w, generator=g).pin_memory() for _ in range(n_img)]
     pr, hy = proj[0].contiguous().pin_memory(), hyps[0].contiguous().pin_memory()
-    pipe = ViewPipeline(v, c, h, w, d, DEV, resident_images=capacity)
+    pipe = ViewPipeline(v, c, h, w, d, DEV, resident_images=capacity, resident_texels=texels)   # texel pool / per-image maps
     regulariser = lambda vol: (-4.0 * vol.mean(0)).contiguous()           # noqa: E731
     windows = [[i] + [j for j in range(min(max(i - 2, 0), n_img - v), min(max(i - 2, 0), n_img - v) + v) if j != i]
                for i in range(n_img)]
@@ -826,6 +827,7 @@ def test_view_pipeline_image_residency_uploads_each_image_once_and_builds_the_sa
         r = sweep.depth_regress(regulariser(vol), hy.to(DEV), want_index=False)
         assert torch.equal(dep, r["depth"].cpu()) and torch.equal(conf, r["conf"].cpu()), "view %d" % i
     assert pipe.lru.hits + pipe.lru.misses == v * len(order)
+    assert (pipe.lru.texels is not None) == texels
     if capacity >= n_img:   # every image is uploaded exactly once, the return visits find theirs resident
         assert pipe.lru.misses == n_img
     else:                   # the return visits re-upload what the walk evicted
