@@ -44,10 +44,10 @@ def _volume_into(out, features, proj_matrices, depth_values, mode, scenes=None, 
     """Plane-major cost volume of every batch item written straight into `out` [B,D,C,h,w]."""
     with torch.no_grad():
         for b in range(features[0].shape[0]):
-            texels, pose, rays = scenes[b] if scenes is not None else _scene(features, proj_matrices, b)
+            texels, pose, rays, slots = scenes[b] if scenes is not None else _scene(features, proj_matrices, b)
             w = kw.get("weights")
             sweep.cost_volume(texels, pose, depth_values[b].contiguous(), mode, plane_major=True, out=out[b], rays=rays,
-                              **{**kw, "weights": None if w is None else w[b]})
+                              view_slots=slots, **{**kw, "weights": None if w is None else w[b]})
 
 
 def _inference_only(what, *tensors):
@@ -71,15 +71,27 @@ def _check(features, proj_matrices, depth_values, num_depth):
         depth_values.shape[1], num_depth)
 
 
+# Opt-in (row f4): a texel_pool.TexelPool.  Set where the feature maps of an image are the same tensor objects for every
+# reference view that uses the image (predict.py sets it together with FeatureCache): an image is then laid out once and the
+# sweeps name their views by pool slot instead of laying out a dense [V,H,W,C] block per reference view and stage.
+TEXEL_POOL = None
+
+
 def _scene(features, proj_matrices, b):
     """What every sweep over one stage of batch item b shares: channels-last texels [V,H,W,C], relative poses
     [V-1,4,4] and the rays rot @ [x,y,1] [V-1,3,H*W] where the kernels cannot form them bit-exactly (sweep.rays_for).  AdaMVS sweeps a stage
     twice (pair volumes, then the weighted product): it builds the scene once."""
     with torch.no_grad():
-        texels = sweep.to_texels([f[b] for f in features])
+        slots = None
+        if TEXEL_POOL is not None and features[0].shape[0] == 1:        # (a batch item's slice is a new tensor every call)
+            found = TEXEL_POOL.lookup(features)
+            if found is not None:
+                texels, slots = found
+        if slots is None:
+            texels = sweep.to_texels([f[b] for f in features])
         pose = sweep.relative_poses(torch.stack([p[b] for p in proj_matrices], 0))
         rays = sweep.rays_for(pose, texels.shape[1], texels.shape[2])
-    return texels, pose, rays
+    return texels, pose, rays, slots
 
 
 def _volume(features, proj_matrices, depth_values, mode, plane_major=False, scenes=None, **kw):
@@ -87,10 +99,10 @@ def _volume(features, proj_matrices, depth_values, mode, plane_major=False, scen
     with torch.no_grad():
         vols = []
         for b in range(features[0].shape[0]):
-            texels, pose, rays = scenes[b] if scenes is not None else _scene(features, proj_matrices, b)
+            texels, pose, rays, slots = scenes[b] if scenes is not None else _scene(features, proj_matrices, b)
             w = kw.get("weights")
             vols.append(sweep.cost_volume(texels, pose, depth_values[b].contiguous(), mode, plane_major=plane_major,
-                                          rays=rays, **{**kw, "weights": None if w is None else w[b]}))
+                                          rays=rays, view_slots=slots, **{**kw, "weights": None if w is None else w[b]}))
         return torch.stack(vols, 0) if len(vols) > 1 else vols[0].unsqueeze(0)
 
 

@@ -110,6 +110,9 @@ def predict_depth(args, model=None):
     cache = None
     if args.feature_cache > 0 and hasattr(model, "feature"):
         cache = FeatureCache(args.feature_cache).attach(model.feature)
+        # the cached maps of an image are the same tensors for every reference view: lay each out once (texel_pool.py)
+        from .texel_pool import TexelPool
+        depthnets.TEXEL_POOL = TexelPool(max(args.feature_cache, 2 * args.view_num))
     views = dataset.MVSDataset(args.data_folder, "val", args.view_num, args.normalize, args)
     os.makedirs(args.output_folder, exist_ok=True)
     written = []
@@ -136,6 +139,8 @@ def predict_depth(args, model=None):
     print("final, total_cnt = {}, total_time = {:3f}".format(len(written), time.time() - t_first))
     if cache:
         print("feature cache:", cache.stats())
+        print("texel pool:", depthnets.TEXEL_POOL.stats())
+        depthnets.TEXEL_POOL = None
         cache.detach()
     return written
 

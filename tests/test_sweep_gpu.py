@@ -943,3 +943,44 @@ def test_texel_pool_slot_validation():
         sweep.cost_volume(tex, pose, hyps[0].to(DEV), view_slots=[0, 1, 3])
     with pytest.raises(ValueError, match="pose"):
         sweep.cost_volume(tex, pose, hyps[0].to(DEV), view_slots=[0, 1])
+
+
+def test_depthnet_texel_pool_lays_each_image_out_once():
+    """depthnets.TEXEL_POOL (texel_pool.TexelPool): reference views that receive the SAME feature-map tensors (FeatureCache)
+    lay an image out once; volumes are bit-identical to the dense-block path, a modified or replaced tensor is laid out again."""
+    from deep3d_aerial_b200 import _lib
+    from deep3d_aerial_b200.texel_pool import TexelPool
+
+    v, c, d, h, w, n_img = 5, 32, 8, 16, 32, 8
+    rig, proj, _, hyps = _scene(v, c, d, h, w, seed=5)
+    g = torch.Generator().manual_seed(17)
+    images = [torch.randn(1, c, h, w, generator=g).to(DEV) for _ in range(n_img)]
+    pr = torch.unbind(proj.to(DEV), 1)
+    hy = hyps.to(DEV)
+    windows = [[i] + [j for j in range(i - 2, i + 3) if j != i] for i in range(2, n_img - 2)]
+    dense = [depthnets._volume([images[j] for j in win], pr, hy, sweep.AGG_VARIANCE) for win in windows]
+    depthnets.TEXEL_POOL = TexelPool(6)                                       # smaller than the walk: slots are recycled
+    try:
+        launches = []
+        for win, want in zip(windows, dense):
+            n0 = _lib.launch_count()
+            got = depthnets._volume([images[j] for j in win], pr, hy, sweep.AGG_VARIANCE)
+            launches.append(_lib.launch_count() - n0)
+            assert torch.equal(got, want)
+        base = launches[0] - v                                                 # everything but the relayouts
+        assert launches == [base + v] + [base + 1] * (len(windows) - 1), launches
+        images[4].mul_(2.0)                                                   # an in-place change bumps the version counter
+        win = windows[-1]
+        n0 = _lib.launch_count()
+        got = depthnets._volume([images[j] for j in win], pr, hy, sweep.AGG_VARIANCE)
+        assert _lib.launch_count() - n0 == base + 1
+        assert torch.equal(got, depthnets._volume([images[j].clone() for j in win], pr, hy, sweep.AGG_VARIANCE))
+        st = depthnets.TEXEL_POOL.stats()
+        assert st["hits"] + st["misses"] == v * (len(windows) + 2)
+        # a batch of two goes the dense way (its per-item slices are new tensors every call)
+        two = [torch.cat([images[j], images[j]], 0) for j in win]
+        pr2 = torch.unbind(proj.to(DEV).repeat(2, 1, 1, 1), 1)
+        both = depthnets._volume(two, pr2, hy.repeat(2, 1), sweep.AGG_VARIANCE)
+        assert torch.equal(both[0], got[0]) and torch.equal(both[1], got[0])
+    finally:
+        depthnets.TEXEL_POOL = None
