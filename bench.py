@@ -556,17 +556,32 @@ def run_cascade(args):
         e.record()
         ev.setdefault(name, []).append(e)
 
-    def step():
+    # Block walk (FeatureCache + texel_pool.TexelPool, what predict.py --feature_cache runs): the views
+    # of a scene block share 4 of their 5 images, whose texels stay resident in a pool of V + 1 slots per stage; a view
+    # lays out only the image new to the walk and names its views by slot.  `walk` = None: every view lays out all V maps
+    # into a dense block (no cache: what a lone reference view costs).
+    for s in stages:
+        s["pool"] = torch.empty((v + 1, s["h"], s["w"], s["c"]), device=dev)
+        sweep.to_texels(s["feats"], out=s["pool"][:v])
+        s["pool"][v].copy_(s["pool"][0])
+
+    def step(walk=None, lay_out=True):
         depth = None
         conf = None
+        slots = None if walk is None else [(walk - j) % (v + 1) for j in range(v)]   # newest image first (the reference)
         for i, s in enumerate(stages):
             mark("s%d_begin" % (i + 1))
-            tex = sweep.to_texels(s["feats"])
+            if walk is None:
+                tex = sweep.to_texels(s["feats"])
+            else:
+                tex = s["pool"]
+                if lay_out:
+                    sweep.to_texels([s["feats"][walk % v]], out=tex[walk % (v + 1):walk % (v + 1) + 1])
             rays = sweep.rays_for(s["pose"], s["h"], s["w"])            # once per stage (depthnets._scene)
             if depth is None:
                 hyps = sweep.depth_samples(sweep.SAMPLES_RANGE, s["d"], (s["h"], s["w"]), device=dev,
                                            dmin=rig.dmin, dmax=rig.dmax)
-                pairs = sweep.cost_volume(tex, s["pose"], hyps, sweep.AGG_PAIR_MEAN, rays=rays)
+                pairs = sweep.cost_volume(tex, s["pose"], hyps, sweep.AGG_PAIR_MEAN, rays=rays, view_slots=slots)
                 conf = torch.stack([sweep.depth_regress(pair_logits[k], hyps, want_index=False)["conf"]
                                     for k in range(v - 1)], 0)
                 del pairs
@@ -576,7 +591,7 @@ def run_cascade(args):
                 conf = sweep.resize_bilinear(conf, (s["h"], s["w"]))       # adamvs.py:498-503, one launch for the V-1 maps
             mark("s%d_sweep" % (i + 1))
             sim = sweep.cost_volume(tex, s["pose"], hyps, sweep.AGG_WEIGHTED_PRODUCT, weights=conf.contiguous(),
-                                    plane_major=True, rays=rays)
+                                    plane_major=True, rays=rays, view_slots=slots)
             mark("s%d_regress" % (i + 1))
             r = None
             held = []                          # planes arrive one at a time, as the GRU regulariser delivers them;
@@ -591,8 +606,19 @@ def run_cascade(args):
             mark("s%d_end" % (i + 1))
         return depth, r["conf"]
 
+    # the dense-block form first (every view lays out all V maps), then the timed block walk
     for _ in range(args.warmup):
         step()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    d0.record()
+    for _ in range(args.steps):
+        step()
+    d1.record()
+    torch.cuda.synchronize()
+    ms_dense = shard.join_max(d0.elapsed_time(d1)) / args.steps
+    for k in range(args.warmup):
+        step(walk=k)
     ev.clear()
     sampler = ClockSampler(local)
     sampler.start()
@@ -601,8 +627,8 @@ def run_cascade(args):
     launches0 = _lib.launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(args.steps):
-        out = step()
+    for k in range(args.steps):
+        out = step(walk=args.warmup + k)
     t1.record()
     torch.cuda.synchronize()
     shard.barrier()
@@ -636,9 +662,7 @@ def run_cascade(args):
     if not args.no_e2e:
         n_e2e = max(3, args.steps)
         pyramid = [torch.randn(s["c"], s["h"], s["w"], generator=g, dtype=torch.float32).pin_memory() for s in stages]
-        ring = [[torch.empty((v + 1, s["c"], s["h"], s["w"]), device=dev) for s in stages]]
-        for k, s in enumerate(stages):
-            ring[0][k][:v].copy_(s["feats"])
+        staging = [torch.empty((s["c"], s["h"], s["w"]), device=dev) for s in stages]   # the uploaded maps, before their relayout
         out_host = [torch.empty((2, full_h, full_w), dtype=torch.float32).pin_memory() for _ in range(2)]
         copy_stream, down_stream = torch.cuda.Stream(), torch.cuda.Stream()
         arrived, consumed = torch.cuda.Event(), torch.cuda.Event()
@@ -654,19 +678,18 @@ def run_cascade(args):
             sink += float(out_host[i & 1][0, 0, 0]) + float(out_host[i & 1][1, 0, 0])
 
         def view(i):
-            """View i uses ring slots i .. i+V-1 (mod V+1); the image of slot i+V (the next view's new one) is uploaded now,
-            under this view's sweeps; its maps go device->host on a third stream under the NEXT view's sweeps, and the
-            host reads view i-1's maps meanwhile: nothing in the loop waits for the view it has just queued."""
-            slot = (i + v) % (v + 1)
+            """View i reads texel-pool slots i, i-1 .. i-V+1 (mod V+1); the image of slot i+1 (the next view's new one) is
+            uploaded AND laid out now, on the copy stream, under this view's sweeps; its maps go device->host on a third
+            stream under the NEXT view's sweeps, and the host reads view i-1's maps meanwhile: nothing in the loop waits
+            for the view it has just queued."""
+            slot = (i + 1) % (v + 1)
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed)                   # the view that last read this slot is done with it
-                for k in range(3):
-                    ring[0][k][slot].copy_(pyramid[k], non_blocking=True)
+                for k, s in enumerate(stages):
+                    staging[k].copy_(pyramid[k], non_blocking=True)
+                    sweep.to_texels([staging[k]], out=s["pool"][slot:slot + 1])
                 arrived.record()
-            order = [(i + j) % (v + 1) for j in range(v)]
-            for k, s in enumerate(stages):
-                s["feats"] = ring[0][k][order]                     # (gathers the V maps: stands in for FeatureNet's outputs)
-            dep, conf = step()
+            dep, conf = step(walk=i, lay_out=False)
             consumed.record()
             computed.record()
             torch.cuda.current_stream().wait_event(arrived)        # the next view needs the image that just arrived
@@ -695,7 +718,8 @@ def run_cascade(args):
         e2e = {"value": shard.join_sum(vox * n_e2e) / dt / 1e9, "unit": "Gvoxel/s", "ms_per_step": dt / n_e2e * 1e3,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host[0].numel() * 4, "steps": n_e2e,
                "timer": "host wall clock", "stream": "one new image (feature pyramid of 3 maps) per reference view, "
-               "uploaded under the view's sweeps into a ring of V + 1 resident images; the maps of view i come back under view i+1"}
+               "uploaded and laid out under the view's sweeps into texel pools of V + 1 resident images; the maps of view i "
+               "come back under view i+1"}
     if rank != 0:
         return None
     cpu = None
@@ -724,7 +748,11 @@ def run_cascade(args):
                                "pair volumes + weighted product + streaming soft-argmax + resampling",
                    "voxels_per_view": vox, "algorithmic_bytes_per_view": sum(bytes_stage),
                    "l2": "every volume (1.3-2.6 GB) exceeds the 126 MB L2", "views_per_step_per_gpu": 1,
-                   "stream_batch_planes": batch_planes},
+                   "stream_batch_planes": batch_planes,
+                   "views": "a block walk: the view's five images live as texels in a pool of V + 1 slots per stage and only "
+                            "the image new to the walk is laid out (FeatureCache + TexelPool, predict.py --feature_cache); "
+                            "ms_per_step_dense_block is the same view laying out all five maps (no cache)"},
+        "ms_per_step_dense_block": ms_dense,
         "ref_views_per_s": world * 1e3 / ms_step, "kernel_ms": kernel_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "weighted-product sweep, stage %d" % (dom + 1),
@@ -921,9 +949,11 @@ def run_fuse(args):
 def _brief(line):
     """What the headline line keeps of another workload's line."""
     keep = ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "ref_views_per_s", "kernel_ms", "roofline", "e2e",
-            "cpu_baseline", "gpu_launches", "note")
+            "cpu_baseline", "gpu_launches", "note", "ms_per_step_dense_block")
     out = {k: line[k] for k in keep if k in line}
     out["workload"] = line["config"]["workload"]
+    if "views" in line["config"]:
+        out["views"] = line["config"]["views"]
     return out
 
 
