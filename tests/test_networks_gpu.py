@@ -75,8 +75,18 @@ def _run_stage(net, g, k, feats, proj, hyps, conf_in=None):
     return out, rep
 
 
+@pytest.fixture(params=[False, True], ids=["dense-block", "texel-pool"])
+def texel_pool(request):
+    """Both ways a DepthNet hands its views to the sweeps: a dense [V,H,W,C] block laid out per call, or slots of a per-image
+    texel pool (depthnets.TEXEL_POOL, what predict.py --feature_cache installs)."""
+    from deep3d_aerial_b200.texel_pool import TexelPool
+    depthnets.TEXEL_POOL = TexelPool(8) if request.param else None
+    yield depthnets.TEXEL_POOL
+    depthnets.TEXEL_POOL = None
+
+
 @pytest.mark.parametrize("net", ["cas", "red", "ada"])
-def test_every_stage_on_the_reference_s_own_stage_inputs(net):
+def test_every_stage_on_the_reference_s_own_stage_inputs(net, texel_pool):
     g = load_golden("net_" + net)
     for k in (1, 2, 3):
         feats, proj, hyps = _stage_inputs(g, k)
@@ -96,6 +106,8 @@ def test_every_stage_on_the_reference_s_own_stage_inputs(net):
             first = torch.stack([c[0, 0] for c in out["pair_confidence"][:len(feats) - 1]]).cpu()
             assert int(g["s%d_pair_conf_out_len" % k]) == len(out["pair_confidence"])
             assert float((first - g["s%d_pair_conf_out_first" % k]).abs().max()) < 1e-5
+    if texel_pool is not None:
+        assert texel_pool.stats()["misses"] > 0 and len(texel_pool.pools) == 3          # the sweeps did go through the pools
 
 
 @pytest.mark.parametrize("net", ["cas", "red", "ada"])
