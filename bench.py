@@ -492,6 +492,9 @@ def run_ours(args):
     }
     if e2e:
         line["e2e"] = e2e
+    if mode == "gwc":
+        line["note"] = ("group-wise correlation has no body in the reference (a commented-out call, adamvs.py:271,295): parity "
+                        "for this mode is UNPINNED by the reference; the oracle restates it by analogy with adamvs.py:473")
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(wl)
     return line
