@@ -132,7 +132,7 @@ class ViewPipeline:
                 "out": torch.empty((2, h, w), dtype=torch.float32).pin_memory(),
                 "copied": torch.cuda.Event(), "free": torch.cuda.Event(), "done": torch.cuda.Event(),
             } for _ in range(slots)]
-            self.texels = torch.empty((v, h, w, c), device=self.dev)
+            self.texels = None                                # dense [V,H,W,C] block: only views submitted without image ids need it
             self.volume = torch.empty((cout, d, h, w), device=self.dev)
         self._next = 0
         self._pending = collections.deque()
@@ -203,6 +203,8 @@ class ViewPipeline:
                 sweep.cost_volume(self.lru.texels, s["pose"], s["hyps"], self.mode, groups=self.groups, out=self.volume,
                                   variant=self.variant, rays=s["rays"], view_slots=s["view_slots"])
             else:
+                if self.texels is None:
+                    self.texels = torch.empty((v, h, w, c), device=self.dev)
                 sweep.to_texels(s["maps"], out=self.texels)
             if s["ids"] is not None:                          # (the sweep itself is the pool's last reader)
                 read = torch.cuda.Event()

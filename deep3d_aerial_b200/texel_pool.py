@@ -22,6 +22,8 @@ from . import sweep
 
 
 class TexelPool:
+    _cuda_only = True      # (the CPU test of the slot bookkeeping clears it and substitutes the relayout)
+
     def __init__(self, capacity: int = 16):
         if capacity < 2:
             raise ValueError("capacity must be >= 2")
@@ -45,7 +47,7 @@ class TexelPool:
         """maps: the V feature maps of one reference view, [C,H,W] or [1,C,H,W] fp32 CUDA tensors of one shape -> (pool
         [S,H,W,C], slot of every map).  None when the view does not fit the pool (the caller lays out a dense block)."""
         first = maps[0]
-        if any((not m.is_cuda) or m.dtype != torch.float32 or m.shape[-3:] != first.shape[-3:] or m.device != first.device
+        if any((self._cuda_only and not m.is_cuda) or m.dtype != torch.float32 or m.shape[-3:] != first.shape[-3:] or m.device != first.device
                or m.numel() != first.shape[-3] * first.shape[-2] * first.shape[-1] for m in maps):
             return None
         st = self._state(first)
