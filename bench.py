@@ -982,7 +982,7 @@ def main():
             import torch
             extra = {}
             for name, fn, over in (("cfg4", run_ours, dict(workload="cfg4", steps=8, warmup=3, no_e2e=True)),
-                                   ("cfg3", run_cascade, dict(steps=5, warmup=3)),
+                                   ("cfg3", run_cascade, dict(steps=10, warmup=3)),
                                    ("cfg5", run_scene_block, dict(block_views=16, warmup=3))):
                 sub = copy.copy(args)
                 for k, val in over.items():
