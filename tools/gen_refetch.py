@@ -245,7 +245,7 @@ def block_tok(cpt, shift=False):
     (low 16 bits of the two round-down-add results); address and border handling live here, on the rare path.
     shift: A = a - ref (the variance volume of the long sweeps, see rebuild_lines)."""
     n = 4 * cpt
-    old, key, base, rowb, hw, wid, hei, wm1, hm1, vplus1, texb, texb16 = (n + i for i in range(12))
+    old, key, base, rowb, vtex, wid, hei, wm1, hm1, vplus1, texb, texb16 = (n + i for i in range(12))
     ref0 = n + 12
     L = []
     A = L.append
@@ -259,7 +259,7 @@ def block_tok(cpt, shift=False):
     A("bfe.s32 x0, %%%d, 0, 16;" % key)
     A("bfe.s32 y0, %%%d, 16, 16;" % key)
     A("mad.lo.s32 t, y0, %%%d, x0;" % wid)
-    A("add.s32 t, t, %%%d;" % hw)                 # + the texel index at which this view starts in `base` (SweepParams.view_tex)
+    A("add.s32 t, t, %%%d;" % vtex)                 # + the texel index at which this view starts in `base` (SweepParams.view_tex)
     A("mad.wide.s32 pa, t, %%%d, %%%d;" % (texb, base))
     A("cvt.u64.u32 w, %%%d;" % rowb)
     A("add.s64 pc, pa, w;")
@@ -340,7 +340,7 @@ def block_tok_split(cpt):
     short sweeps of the cascade need, where a footprint lasts 1-3 planes and the re-fetch latency, paid once per
     view in the one-block form, is half of all stall samples (profiles/ncu_r1_cfg3.txt)."""
     n = 4 * cpt
-    old, mv, key, base, rowb, hw, wid, hei, wm1, hm1, vplus1, texb, texb16 = (n + i for i in range(13))
+    old, mv, key, base, rowb, vtex, wid, hei, wm1, hm1, vplus1, texb, texb16 = (n + i for i in range(13))
     L = []
     A = L.append
     A("{")
@@ -354,7 +354,7 @@ def block_tok_split(cpt):
     A("bfe.s32 x0, %%%d, 0, 16;" % key)
     A("bfe.s32 y0, %%%d, 16, 16;" % key)
     A("mad.lo.s32 t, y0, %%%d, x0;" % wid)
-    A("add.s32 t, t, %%%d;" % hw)                 # + the texel index at which this view starts in `base` (SweepParams.view_tex)
+    A("add.s32 t, t, %%%d;" % vtex)                 # + the texel index at which this view starts in `base` (SweepParams.view_tex)
     A("mad.wide.s32 pa, t, %%%d, %%%d;" % (texb, base))
     A("cvt.u64.u32 w, %%%d;" % rowb)
     A("add.s64 pc, pa, w;")
@@ -531,7 +531,7 @@ def block_dot(cpt):
     four DOT PRODUCTS PA = sum ref_c A_c, PB, PC, PD -- 4 registers per view instead of 16, and 3 FMAs per view and
     plane instead of 3 per channel.  The corners live in block-local registers only while the dots are formed."""
     n = 4                                   # outputs: PA, PB, PC, PD
-    old, key, base, rowb, hw, wid, hei, wm1, hm1, vplus1, texb, texb16 = (n + i for i in range(12))
+    old, key, base, rowb, vtex, wid, hei, wm1, hm1, vplus1, texb, texb16 = (n + i for i in range(12))
     ref0 = n + 12
     L = []
     A = L.append
@@ -546,7 +546,7 @@ def block_dot(cpt):
     A("bfe.s32 x0, %%%d, 0, 16;" % key)
     A("bfe.s32 y0, %%%d, 16, 16;" % key)
     A("mad.lo.s32 t, y0, %%%d, x0;" % wid)
-    A("add.s32 t, t, %%%d;" % hw)                 # + the texel index at which this view starts in `base` (SweepParams.view_tex)
+    A("add.s32 t, t, %%%d;" % vtex)                 # + the texel index at which this view starts in `base` (SweepParams.view_tex)
     A("mad.wide.s32 pa, t, %%%d, %%%d;" % (texb, base))
     A("cvt.u64.u32 w, %%%d;" % rowb)
     A("add.s64 pc, pa, w;")
