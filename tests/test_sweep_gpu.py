@@ -984,3 +984,32 @@ def test_depthnet_texel_pool_lays_each_image_out_once():
         assert torch.equal(both[0], got[0]) and torch.equal(both[1], got[0])
     finally:
         depthnets.TEXEL_POOL = None
+
+
+@pytest.mark.parametrize("c,d,scale,mode", [(32, 16, 4, sweep.AGG_VARIANCE), (16, 8, 2, sweep.AGG_WEIGHTED_PRODUCT),
+                                            (8, 8, 1, sweep.AGG_WEIGHTED_PRODUCT)])
+def test_texel_pool_at_full_size_is_bit_identical_to_the_dense_block(c, d, scale, mode):
+    """BASELINE.json's full image sizes (the three cascade resolutions of 1856x2752): views in scattered slots of a 7-slot
+    pool -- texel offsets of up to 30 M texels / 1 GB -- against the dense block, bit for bit."""
+    v = 5
+    rig = synth.make_rig(num_views=v)
+    h, w = 2752 // scale, 1856 // scale
+    g = torch.Generator().manual_seed(23)
+    pose = sweep.relative_poses(torch.from_numpy(rig.proj(scale)).to(DEV))
+    if mode == sweep.AGG_VARIANCE:
+        hyps = synth.uniform_hypotheses(rig.dmin, rig.dmax, 384)[100:100 + d].to(DEV).contiguous()
+        kw = {}
+    else:
+        cur = synth.smooth_depth_map(rig, h, w, seed=2).to(DEV)
+        hyps = synth.per_pixel_hypotheses(cur, d, scale * (rig.dmax - rig.dmin) / 384).contiguous()
+        kw = {"weights": torch.rand(v - 1, h, w, generator=g).to(DEV), "plane_major": True}
+    slots = [5, 0, 6, 2, 3]
+    pool = torch.full((7, h, w, c), float("nan"), device=DEV)
+    tex = torch.empty((v, h, w, c), device=DEV)
+    for i, s in enumerate(slots):
+        fmap = torch.randn(c, h, w, generator=g).to(DEV)
+        sweep.to_texels([fmap], out=tex[i:i + 1])
+        pool[s].copy_(tex[i])
+    dense = sweep.cost_volume(tex, pose, hyps, mode, **kw)
+    pooled = sweep.cost_volume(pool, pose, hyps, mode, view_slots=slots, **kw)
+    assert torch.equal(pooled, dense) and bool(torch.isfinite(pooled).all())
