@@ -24,7 +24,20 @@ for (v, c, d, h, w) in ((5, 8, 8, 45, 67), (3, 16, 11, 33, 50), (5, 8, 3, 70, 6)
     extra = []
     if c == 32:
         extra = [sweep.cost_volume(tex, pose, uni, sweep.AGG_GROUP_CORR, groups=8), sweep.cost_volume(tex, pose, hyps, sweep.AGG_PAIR_MEAN)]
+    # the same views as slots of a texel pool allocated to the byte: the reference in the LAST slot, a source in the first
+    slots = [v + 1, 0] + list(range(2, v))
+    pool = torch.empty((v + 2, h, w, c), device=dev)
+    for i, sl in enumerate(slots):
+        pool[sl].copy_(tex[i])
+    pooled = [sweep.cost_volume(pool, pose, hyps, sweep.AGG_WEIGHTED_PRODUCT, weights=wt, view_slots=slots),
+              sweep.cost_volume(pool, pose, uni, sweep.AGG_VARIANCE, view_slots=slots),
+              sweep.cost_volume(pool, pose, hyps, sweep.AGG_VARIANCE, view_slots=slots, variant=1)]
+    if c == 32:
+        pooled += [sweep.cost_volume(pool, pose, uni, sweep.AGG_GROUP_CORR, groups=8, view_slots=slots),
+                   sweep.cost_volume(pool, pose, hyps, sweep.AGG_PAIR_MEAN, view_slots=slots)]
+    same = ["%.1e" % float((a - b).abs().max() / b.abs().max()) for a, b in zip(pooled, [outs[0], var[0], var[3]] + extra)]
     torch.cuda.synchronize()
+    print("texel pool vs the dense block (0 = the same kernel served both; sweep_lean's shapes fall through to sweep_base):", same)
     print(v, c, d, h, w, "weighted product:", ["%.1e" % float((o - outs[0]).abs().max()) for o in outs],
           "variance (uniform, per pixel) vs baseline kernel:", "%.1e %.1e" % (float((var[0] - var[1]).abs().max()),
                                                                             float((var[2] - var[3]).abs().max())),
